@@ -1,0 +1,132 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical state."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ivfpq_oracle as O, build_state as B
+from helpers import make_index, tie_free_rows, assert_close_results
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,d,C,n,k,n_probe", [
+    (8, 32, 16, 3000, 10, 4),
+    (64, 128, 32, 6000, 100, 8),
+    (32, 64, 8, 2000, 1, 3),
+    (120, 240, 16, 4000, 100, 16),
+])
+@pytest.mark.parametrize("smart", [False, True])
+def test_integer_kat_exact(cuda_device, M, d, C, n, k, n_probe, smart):
+    """Integer-valued state: every score is exact, so values must be identical and ids identical
+    on every query that is tie-free at the k-th boundary."""
+    st, queries = B.integer_state(d, M, C, n, seed=M + k)
+    st.n_probe, st.use_smart_probing = n_probe, smart
+    x = queries(64)
+    ov, oi, oa = O.search(st, x, k=k + 1, return_address=True)
+    ix = make_index(st)
+    v, i, a = ix.search(x.cuda(), k=k, return_address=True)
+    v, i, a = v.cpu().numpy(), i.cpu().numpy(), a.cpu().numpy()
+    assert np.array_equal(v, ov[:, :k])                       # values are exact whatever the tie order
+    ok = tie_free_rows(ov, k)
+    assert ok.sum() > 0
+    assert np.array_equal(i[ok], oi[ok, :k])
+    assert np.array_equal(a[ok], oa[ok, :k])
+    # with the shared total order (score desc, address asc) even tied rows agree
+    assert np.array_equal(a, oa[:, :k])
+
+
+@pytest.mark.parametrize("distance,M,d", [("euclidean", 8, 128), ("euclidean", 64, 128), ("cosine", 24, 96)])
+def test_randn_close(cuda_device, distance, M, d):
+    torch.manual_seed(7)
+    base = torch.randn(d, 8000)
+    st = B.build_state(base, M, 32, distance=distance, vq_iters=3, pq_iters=2, n_train=4000)
+    st.n_probe = 8
+    x = torch.randn(d, 100)
+    for smart in (False, True):
+        st.use_smart_probing = smart
+        ov, oi = O.search(st, x, k=50)
+        ix = make_index(st)
+        v, i = ix.search(x.cuda(), k=50)
+        assert_close_results(v.cpu().numpy(), i.cpu().numpy(), ov, oi, rtol=1e-3, min_overlap=0.995)
+
+
+def test_fewer_than_k_and_empty_cells(cuda_device):
+    st, queries = B.integer_state(32, 8, 64, 40, seed=3)     # 40 vectors in 64 cells: most cells empty
+    st.n_probe, st.use_smart_probing = 8, False
+    x = queries(16)
+    ov, oi, oa = O.search(st, x, k=20, return_address=True)
+    ix = make_index(st)
+    v, i, a = ix.search(x.cuda(), k=20, return_address=True)
+    assert np.array_equal(v.cpu().numpy(), ov)
+    assert np.array_equal(a.cpu().numpy(), oa)
+    assert np.array_equal(i.cpu().numpy(), oi)
+    assert (oi == -1).any() and np.isinf(ov).any()
+
+
+def test_is_empty_holes(cuda_device):
+    st, queries = B.integer_state(32, 8, 8, 1000, seed=5)
+    rng = np.random.default_rng(0)
+    live = np.flatnonzero(st.is_empty == 0)
+    holes = rng.choice(live, 200, replace=False)
+    st.is_empty[holes] = 1
+    st.n_probe, st.use_smart_probing = 4, False
+    x = queries(32)
+    ov, oi, oa = O.search(st, x, k=10, return_address=True)
+    ix = make_index(st)
+    v, i, a = ix.search(x.cuda(), k=10, return_address=True)
+    assert np.array_equal(a.cpu().numpy(), oa) and np.array_equal(v.cpu().numpy(), ov)
+    assert not np.isin(a.cpu().numpy(), holes).any()
+
+
+@pytest.mark.parametrize("k", [1, 10, 100, 256, 1024])
+def test_k_sweep(cuda_device, k):
+    st, queries = B.integer_state(64, 16, 8, 5000, seed=11, lo=-8, hi=9)
+    st.n_probe, st.use_smart_probing = 6, False
+    x = queries(8)
+    ov, oi, oa = O.search(st, x, k=k, return_address=True)
+    ix = make_index(st)
+    v, i, a = ix.search(x.cuda(), k=k, return_address=True)
+    assert np.array_equal(v.cpu().numpy(), ov)
+    assert np.array_equal(a.cpu().numpy(), oa)
+
+
+def test_reference_layout_op(cuda_device):
+    """fn.IVFPQTopk.topk drop-in (reference storage layout, reference LUT layout, reference sum order):
+    values are bit-identical to the oracle's m-ascending fp32 sums even on randn data."""
+    import torchpq_b200 as T
+    torch.manual_seed(3)
+    base = torch.randn(64, 5000)
+    st = B.build_state(base, 16, 16, vq_iters=2, pq_iters=2)
+    st.n_probe, st.use_smart_probing = 5, True
+    x = torch.randn(64, 40)
+    xx, sims, cells, npl = O.coarse_probe(st, x)
+    lut = O.precompute_adc(xx, torch.from_numpy(st.pq_codebook), st.distance)
+    cs, cz = st.cell_start[cells.numpy()], st.cell_size[cells.numpy()]
+    ov, oa = O.ivfpq_topk(st.storage, lut.numpy(), st.is_empty, cs, cz, npl.numpy(), 30)
+    op = T.fn.IVFPQTopk(16)
+    v, a = op.topk(torch.from_numpy(st.storage).cuda(), lut.cuda(), torch.from_numpy(cs).cuda(),
+                   torch.from_numpy(cz).cuda(), torch.from_numpy(st.is_empty).cuda(), npl.cuda(), k=30)
+    assert np.array_equal(v.cpu().numpy(), ov)
+    assert np.array_equal(a.cpu().numpy(), oa)
+
+
+def test_lut_and_coarse(cuda_device):
+    import torchpq_b200 as T
+    torch.manual_seed(5)
+    for distance in ("euclidean", "cosine"):
+        base = torch.randn(96, 3000)
+        st = B.build_state(base, 24, 64, distance=distance, vq_iters=2, pq_iters=1)
+        st.n_probe = 16
+        x = torch.randn(96, 50)
+        xx, sims, cells, npl = O.coarse_probe(st, x)
+        xg = x.cuda()
+        if distance == "cosine":
+            xg = T.fn.normalize(xg)
+            assert torch.allclose(xg.cpu(), xx, rtol=1e-5, atol=1e-7)
+        lut = T.fn.precompute_adc(xg, torch.from_numpy(st.pq_codebook).cuda(), distance).cpu()
+        olut = O.precompute_adc(xx, torch.from_numpy(st.pq_codebook), distance)
+        assert torch.allclose(lut, olut, rtol=1e-4, atol=1e-4)
+        gs, gc, gn = T.fn.coarse_probe(xg, torch.from_numpy(st.vq_codebook).cuda(), 16, True, 30.0)
+        assert torch.allclose(gs.cpu(), sims, rtol=1e-4, atol=1e-3)
+        assert (gc.cpu() == cells).float().mean() > 0.99
+        assert (gn.cpu() == npl).float().mean() > 0.98

@@ -1,0 +1,225 @@
+// Query preparation and coarse probing.
+//
+// Replaces, for IVFPQIndex.search (torchpq/index/IVFPQIndex.py:474-512):
+//   util.normalize                          torchpq/util.py:38-43
+//   metric.negative_squared_l2_distance     torchpq/metric.py:74-94   (cuBLAS sgemm + 4 elementwise passes)
+//   fn.Topk -> top32_select / topk_select   torchpq/fn/Topk.py:43-67, kernels/cuda/top32_select.cu:483-636
+//   smart probing                           torchpq/index/IVFPQIndex.py:499-512 (~8 torch launches)
+// with three launches: squared norms, a tiled fp32 GEMM with the "*2 - |x|^2 - |c|^2"
+// epilogue fused, and a warp-per-query top-n_probe select with smart probing fused.
+#include "common.cuh"
+
+namespace tpq {
+
+// out[j] = sum_i x[i, j]^2  (separately rounded squares, ascending i -- torch's (a ** 2).sum(dim=-2))
+__global__ void col_sqnorm_kernel(const float* __restrict__ x, int d, int n, float* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float s = 0.f;
+  for (int i = 0; i < d; ++i) {
+    float v = x[(size_t)i * n + j];
+    s = __fadd_rn(s, __fmul_rn(v, v));
+  }
+  out[j] = s;
+}
+
+// out[:, j] = x[:, j] / (||x[:, j]||_2 + 1e-9)   (util.py:38-43)
+__global__ void normalize_columns_kernel(const float* __restrict__ x, int d, int n, float* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float s = 0.f;
+  for (int i = 0; i < d; ++i) {
+    float v = x[(size_t)i * n + j];
+    s = fmaf(v, v, s);
+  }
+  float nrm = __fadd_rn(sqrtf(s), 1e-9f);
+  for (int i = 0; i < d; ++i) out[(size_t)i * n + j] = __fdiv_rn(x[(size_t)i * n + j], nrm);
+}
+
+// sims[q, c] = ((2 * sum_i x[i,q] * cb[i,c]) - xn[q]) - cn[c]        (metric.py:75-94)
+// 128x128 tile, 256 threads, 8x8 micro-tile split in two 4-wide halves so that
+// shared-memory reads are conflict-free float4s; K step 16.
+constexpr int GB = 128, GK = 16;
+__global__ void __launch_bounds__(256)
+coarse_gemm_kernel(const float* __restrict__ x, const float* __restrict__ cb,
+                   const float* __restrict__ xn, const float* __restrict__ cn,
+                   int d, int nq, int C, float* __restrict__ sims) {
+  __shared__ __align__(16) float As[GK][GB];
+  __shared__ __align__(16) float Bs[GK][GB];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int q0 = blockIdx.y * GB, c0 = blockIdx.x * GB;
+  float acc[8][8];
+  #pragma unroll
+  for (int i = 0; i < 8; ++i)
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < d; k0 += GK) {
+    // 16 x 128 floats per operand = 2048 elements / 256 threads = 8 each
+    #pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      int e = r * 256 + tid;
+      int kk = e >> 7, col = e & 127;
+      int gk = k0 + kk;
+      As[kk][col] = (gk < d && q0 + col < nq) ? x[(size_t)gk * nq + q0 + col] : 0.f;
+      Bs[kk][col] = (gk < d && c0 + col < C) ? cb[(size_t)gk * C + c0 + col] : 0.f;
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      #pragma unroll
+      for (int i = 0; i < 8; ++i)
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  #pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int q = q0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (q >= nq) continue;
+    float a2 = xn[q];
+    #pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      int c = c0 + jh * 64 + tx * 4;
+      float o[4];
+      #pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y = __fmul_rn(acc[i][jh * 4 + j], 2.f);
+        y = __fsub_rn(y, a2);
+        o[j] = (c + j < C) ? __fsub_rn(y, cn[c + j]) : 0.f;
+      }
+      float* dst = sims + (size_t)q * C + c;
+      if (c + 3 < C && (C & 3) == 0) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      else for (int j = 0; j < 4 && c + j < C; ++j) dst[j] = o[j];
+    }
+  }
+}
+
+// One warp per query: top-n_probe of sims[q, :] (descending; ties -> lower cell index first),
+// then the smart-probing entropy (IVFPQIndex.py:499-512).
+__global__ void __launch_bounds__(128)
+probe_select_kernel(const float* __restrict__ sims, int nq, int C, int n_probe, int kp,
+                    int smart, float temperature,
+                    float* __restrict__ probe_sims, int64_t* __restrict__ cells,
+                    int64_t* __restrict__ n_probe_list) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (q >= nq) return;                                   // whole warp exits together
+  uint64_t* base = reinterpret_cast<uint64_t*>(smem) + (size_t)warp * (kp + kTopkBuf);
+  WarpTopK tk;
+  tk.init(base, base + kp, kp, n_probe, lane);
+  const float* row = sims + (size_t)q * C;
+  uint64_t thr = 0;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    int c = c0 + lane;
+    bool ok = c < C;
+    uint64_t key = ok ? make_key(row[c], (uint32_t)c) : 0ull;
+    if (tk.push(ok && key > thr, key, lane)) thr = tk.kth();
+  }
+  tk.flush(lane);
+  float* ps = probe_sims + (size_t)q * n_probe;
+  int64_t* pc = cells + (size_t)q * n_probe;
+  for (int j = lane; j < n_probe; j += 32) {
+    uint64_t key = tk.list[j];
+    ps[j] = key ? key_score(key) : -INFINITY;
+    pc[j] = key ? (int64_t)key_addr(key) : 0;            // fewer cells than n_probe: reference pads index 0
+  }
+  if (!(smart && n_probe > 1)) {
+    if (lane == 0) n_probe_list[q] = n_probe;            // IVFPQIndex.py:511-512
+    return;
+  }
+  // p = softmax(-sqrt|s| / T);  H = -sum(p * log2 p / log2 n_probe);  n = ceil(H * n_probe)
+  float mx = -INFINITY;
+  for (int j = lane; j < n_probe; j += 32) {
+    uint64_t key = tk.list[j];
+    float s = key ? key_score(key) : -INFINITY;
+    float z = __fdiv_rn(-sqrtf(fabsf(s)), temperature);
+    mx = fmaxf(mx, z);
+  }
+  #pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < n_probe; j += 32) {
+    uint64_t key = tk.list[j];
+    float s = key ? key_score(key) : -INFINITY;
+    float z = __fdiv_rn(-sqrtf(fabsf(s)), temperature);
+    sum += expf(z - mx);
+  }
+  #pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float lg = log2f((float)n_probe);
+  float h = 0.f;
+  for (int j = lane; j < n_probe; j += 32) {
+    uint64_t key = tk.list[j];
+    float s = key ? key_score(key) : -INFINITY;
+    float z = __fdiv_rn(-sqrtf(fabsf(s)), temperature);
+    float p = __fdiv_rn(expf(z - mx), sum);
+    h += __fdiv_rn(__fmul_rn(p, log2f(p)), lg);          // 0 * -inf = NaN, as in the reference
+  }
+  #pragma unroll
+  for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  if (lane == 0) {
+    float v = ceilf(__fmul_rn(-h, (float)n_probe));
+    // CUDA's float->int64 conversion of NaN yields INT64_MIN, which is what the reference's
+    // `.long()` produces on device; the scan then reads it as (int)0 -> one probe.
+    n_probe_list[q] = isnan(v) ? (int64_t)0x8000000000000000ull : (int64_t)v;
+  }
+}
+
+}  // namespace tpq
+
+using namespace tpq;
+
+extern "C" int tpq_normalize_columns(const float* x_dn, int d, int nq, float* out_dn, void* stream) {
+  TPQ_REQUIRE(x_dn && out_dn && d > 0 && nq >= 0, "tpq_normalize_columns: bad argument");
+  if (nq == 0) return TPQ_OK;
+  normalize_columns_kernel<<<(nq + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x_dn, d, nq, out_dn);
+  TPQ_LAUNCH_CHECK("normalize_columns_kernel");
+  return TPQ_OK;
+}
+
+extern "C" size_t tpq_coarse_workspace_bytes(int d, int nq, int n_cells) {
+  (void)d;
+  return align_up((size_t)nq * n_cells * 4, 256) + align_up((size_t)nq * 4, 256) + align_up((size_t)n_cells * 4, 256);
+}
+
+extern "C" int tpq_coarse_probe(const float* x_dn, const float* vq_codebook, int d, int nq, int n_cells,
+                                int n_probe, int smart, float temperature,
+                                float* probe_sims, int64_t* cells, int64_t* n_probe_list,
+                                void* ws, size_t ws_bytes, void* stream) {
+  TPQ_REQUIRE(x_dn && vq_codebook && probe_sims && cells && n_probe_list, "tpq_coarse_probe: null pointer");
+  TPQ_REQUIRE(d > 0 && nq >= 0 && n_cells > 0, "tpq_coarse_probe: bad sizes d=%d nq=%d C=%d", d, nq, n_cells);
+  TPQ_REQUIRE(n_probe >= 1 && n_probe <= n_cells, "n_probe=%d must be in [1, n_cells=%d]", n_probe, n_cells);
+  if (n_probe > 1024) { set_error("n_probe=%d > 1024 is not supported", n_probe); return TPQ_ERR_UNSUPPORTED; }
+  if (ws_bytes < tpq_coarse_workspace_bytes(d, nq, n_cells) || !ws) {
+    set_error("tpq_coarse_probe: workspace too small (%zu < %zu)", ws_bytes, tpq_coarse_workspace_bytes(d, nq, n_cells));
+    return TPQ_ERR_WORKSPACE;
+  }
+  if (nq == 0) return TPQ_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+  float* sims = reinterpret_cast<float*>(w);  w += align_up((size_t)nq * n_cells * 4, 256);
+  float* xn = reinterpret_cast<float*>(w);    w += align_up((size_t)nq * 4, 256);
+  float* cn = reinterpret_cast<float*>(w);
+  col_sqnorm_kernel<<<(nq + 255) / 256, 256, 0, st>>>(x_dn, d, nq, xn);
+  col_sqnorm_kernel<<<(n_cells + 255) / 256, 256, 0, st>>>(vq_codebook, d, n_cells, cn);
+  dim3 grid((n_cells + GB - 1) / GB, (nq + GB - 1) / GB);
+  coarse_gemm_kernel<<<grid, 256, 0, st>>>(x_dn, vq_codebook, xn, cn, d, nq, n_cells, sims);
+  TPQ_LAUNCH_CHECK("coarse_gemm_kernel");
+  const int kp = next_pow2(n_probe < 32 ? 32 : n_probe);
+  const int wpb = 4;
+  size_t smem = (size_t)wpb * (kp + kTopkBuf) * sizeof(uint64_t);
+  TPQ_CUDA(cudaFuncSetAttribute(probe_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_select_kernel<<<(nq + wpb - 1) / wpb, wpb * 32, smem, st>>>(sims, nq, n_cells, n_probe, kp, smart, temperature,
+                                                                   probe_sims, cells, n_probe_list);
+  TPQ_LAUNCH_CHECK("probe_select_kernel");
+  return TPQ_OK;
+}

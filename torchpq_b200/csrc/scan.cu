@@ -1,0 +1,470 @@
+// The hot path: fused IVF list scan + top-k over the scan layout (relayout.cu).
+//
+// Replaces the reference's ivfpq_topk kernel (torchpq/kernels/cuda/ivfpq_topk.cu:822-971,
+// >90 % of search time there) together with the LUT hand-off, the [nq,n_probe] gathers
+// (IVFPQIndex.py:420-421) and get_id_by_address (container/BaseContainer.py:58-65).
+//
+// Per (query, slice) CTA:
+//   * the query's LUT sits in shared memory TRANSPOSED, lut[g][code][s] (g = m / 64,
+//     s = m % 64, fp32, 256-byte rows), so an entry's byte address is
+//         g*65536 + code*256 + s*4
+//     and, because the codes are lane-rotated (relayout.cu), lane l at step t reads slot
+//     s = 32*(h&1) + ((l + t) & 31): 32 lanes -> 32 distinct banks, zero conflicts.
+//   * one PRMT builds the whole address: byte 1 = the code byte, byte 0 = the lane's
+//     precomputed slot offset, bytes 2..3 = sign-replicated zero; the half-group and
+//     group offsets are LDS immediates.  Inner loop = PRMT + LDS + FADD per code byte.
+//   * each warp streams whole 32-vector blocks with coalesced 128-bit loads, software
+//     pipelined one block ahead; top-k is threshold-filtered per warp (WarpTopK) against
+//     a CTA-wide k-th-best, lists tree-merged at the end.
+// Sub-quantizer sums are fp32 in four interleaved partial sums (exact for integer LUTs;
+// ~1e-7 relative otherwise -- the reference's m-ascending order lives in scan_ref.cu).
+#include "common.cuh"
+
+namespace tpq {
+
+// ----------------------------------------------------------------------------- LUT in scan layout (global)
+// lut_scan[q][g][code][s] = LUT[64 g + s][q][code], zero for padding sub-quantizers.
+// Same arithmetic as lut.cu (PQCodec.py:62-75, MultiKMeans.py:183-223).
+__global__ void __launch_bounds__(256)
+lut_scan_kernel(const float* __restrict__ x, const float* __restrict__ cbt, const float* __restrict__ nrm,
+                int d, int M, int MP, int nq, int q_base, int metric, float* __restrict__ lut_scan) {
+  extern __shared__ __align__(16) float xs[];            // [d] query, then [MP] |x_m|^2
+  const int q = q_base + blockIdx.x;
+  const int dsub = d / M;
+  float* a2s = xs + d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) xs[i] = x[(size_t)i * nq + q];
+  __syncthreads();
+  for (int m = threadIdx.x; m < MP; m += blockDim.x) {
+    float a2 = 0.f;
+    if (m < M) for (int i = 0; i < dsub; ++i) { float v = xs[m * dsub + i]; a2 = __fadd_rn(a2, __fmul_rn(v, v)); }
+    a2s[m] = a2;
+  }
+  __syncthreads();
+  const int MG = (MP + 63) / 64;
+  float* out = lut_scan + (size_t)blockIdx.x * MG * 16384;
+  const int m4n = MP / 4;
+  for (int item = threadIdx.x; item < 256 * m4n; item += blockDim.x) {
+    const int c = item / m4n, m0 = (item % m4n) * 4;
+    float o[4];
+    #pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int m = m0 + u;
+      float y = 0.f;
+      if (m < M) {
+        const float* p = cbt + ((size_t)c * MP + m) * dsub;
+        float dot = 0.f;
+        for (int i = 0; i < dsub; ++i) dot = fmaf(xs[m * dsub + i], p[i], dot);
+        y = dot;
+        if (metric == TPQ_METRIC_EUCLIDEAN)
+          y = __fsub_rn(__fsub_rn(__fmul_rn(dot, 2.f), a2s[m]), nrm[(size_t)c * MP + m]);
+      }
+      o[u] = y;
+    }
+    const int g = m0 >> 6, s = m0 & 63;
+    *reinterpret_cast<float4*>(out + (size_t)g * 16384 + c * 64 + s) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ----------------------------------------------------------------------------- scan kernel
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// LUT entry for code byte J of `w`, slot offset byte J of `off`; imm = group/half-group byte offset.
+template <int J>
+__device__ __forceinline__ float lut_at(const uint8_t* lut, uint32_t w, uint32_t off, int imm) {
+  constexpr uint32_t sel = (4u + J) | (uint32_t(J) << 4) | ((8u | (4u + J)) << 8) | ((8u | (4u + J)) << 12);
+  return *reinterpret_cast<const float*>(lut + prmt(w, off, sel) + imm);
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+template <int MP>
+struct BlockRegs {
+  uint32_t w[MP / 4];
+  uint32_t valid;
+  uint32_t addr0;
+};
+
+template <int MP>
+__device__ __forceinline__ void load_block(BlockRegs<MP>& r, const uint8_t* __restrict__ codes,
+                                           const uint32_t* __restrict__ valid, int64_t B, uint32_t addr0, int lane) {
+  const uint4* p = reinterpret_cast<const uint4*>(codes + (size_t)B * (MP * 32)) + lane;
+  #pragma unroll
+  for (int j = 0; j < MP / 16; ++j) {
+    uint4 v = ldg_stream(p + j * 32);
+    r.w[4 * j + 0] = v.x; r.w[4 * j + 1] = v.y; r.w[4 * j + 2] = v.z; r.w[4 * j + 3] = v.w;
+  }
+  r.valid = __ldg(valid + B);
+  r.addr0 = addr0;
+}
+
+template <int MP>
+__device__ __forceinline__ float adc_block(const BlockRegs<MP>& r, const uint32_t (&off)[8], const uint8_t* lut) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  #pragma unroll
+  for (int i = 0; i < MP / 4; ++i) {
+    const int h = i >> 3;                               // half-group (32 sub-quantizers = 8 words)
+    const int imm = (h >> 1) * 65536 + (h & 1) * 128;
+    a0 += lut_at<0>(lut, r.w[i], off[i & 7], imm);
+    a1 += lut_at<1>(lut, r.w[i], off[i & 7], imm);
+    a2 += lut_at<2>(lut, r.w[i], off[i & 7], imm);
+    a3 += lut_at<3>(lut, r.w[i], off[i & 7], imm);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+struct ScanSmem { size_t lut, seg_blk0, seg_addr0, seg_prefix, thr, lists, total; };
+static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp) {
+  ScanSmem s; size_t off = 0;
+  s.lut = off;        off += (size_t)((MP + 63) / 64) * 65536;
+  s.seg_blk0 = off;   off += (size_t)n_probe * 4;
+  s.seg_addr0 = off;  off += (size_t)n_probe * 4;
+  s.seg_prefix = off; off += (size_t)(n_probe + 1) * 4;
+  off = align_up(off, 8);
+  s.thr = off;        off += 8;
+  s.lists = off;      off += (size_t)nw * (kp + kTopkBuf) * 8;
+  s.total = off;
+  return s;
+}
+
+struct ScanArgs {
+  const uint8_t* codes; const uint32_t* valid; const int32_t* cell_block_start; const int64_t* cell_start;
+  const float* lut_scan;          // [nq_chunk][MG][256][64]
+  const int64_t* cells;           // [nq, n_probe]
+  const int64_t* n_probe_list;    // [nq]
+  uint64_t* keys_out;             // [nq, S, k]
+  int nq, q_base, n_probe, k, kp, S;
+};
+
+template <int MP, int NW>
+__global__ void __launch_bounds__(NW * 32, (MP <= 64 ? 2 : 1))
+ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* lut = smem;                                       // L.lut == 0 by construction
+  int32_t*  seg_blk0   = reinterpret_cast<int32_t*>(smem + L.seg_blk0);
+  uint32_t* seg_addr0  = reinterpret_cast<uint32_t*>(smem + L.seg_addr0);
+  int32_t*  seg_prefix = reinterpret_cast<int32_t*>(smem + L.seg_prefix);
+  unsigned long long* cta_thr = reinterpret_cast<unsigned long long*>(smem + L.thr);
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + L.lists);
+  constexpr int MG = (MP + 63) / 64;
+
+  const int qi = blockIdx.x / A.S, slice = blockIdx.x % A.S;  // query within this chunk
+  const int q = A.q_base + qi;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // --- stage LUT (MG * 64 KB, coalesced 16-byte copies)
+  {
+    const float4* src = reinterpret_cast<const float4*>(A.lut_scan + (size_t)qi * MG * 16384);
+    float4* dst = reinterpret_cast<float4*>(lut);
+    #pragma unroll 4
+    for (int i = tid; i < MG * 4096; i += NW * 32) dst[i] = __ldg(src + i);
+  }
+  // --- probe segments (same visiting rules as scan_ref.cu / ivfpq_topk.cu:837-870)
+  int P = (int)A.n_probe_list[q];
+  P = max(1, min(P, A.n_probe));
+  if (warp == 0) {
+    int carry = 0;
+    if (lane == 0) seg_prefix[0] = 0;
+    const int64_t* cq = A.cells + (size_t)q * A.n_probe;
+    for (int j0 = 0; j0 < P; j0 += 32) {
+      const int j = j0 + lane;
+      int nb = 0;
+      if (j < P) {
+        const int64_t c = cq[j];
+        const int64_t s = A.cell_start[c];
+        const bool skip = (j > 0) && (s == A.cell_start[cq[j - 1]]);
+        const int b0 = A.cell_block_start[c];
+        nb = skip ? 0 : A.cell_block_start[c + 1] - b0;
+        seg_blk0[j] = b0;
+        seg_addr0[j] = (uint32_t)s;
+      }
+      int incl = nb;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (j < P) seg_prefix[j + 1] = carry + incl;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  if (tid == 0) *cta_thr = 0ull;
+  WarpTopK tk;
+  tk.init(lists + (size_t)warp * (A.kp + kTopkBuf), lists + (size_t)warp * (A.kp + kTopkBuf) + A.kp, A.kp, A.k, lane);
+  // lane's slot offsets: byte r%4 of off[r/4] = ((lane + r) & 31) * 4
+  uint32_t off[8];
+  #pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t v = 0;
+    #pragma unroll
+    for (int b = 0; b < 4; ++b) v |= (uint32_t)(((lane + 4 * i + b) & 31) * 4) << (8 * b);
+    off[i] = v;
+  }
+  __syncthreads();
+
+  const int total = seg_prefix[P];
+  const int b_begin = (int)(((int64_t)total * slice) / A.S);
+  const int b_end = (int)(((int64_t)total * (slice + 1)) / A.S);
+  int seg = 0;
+  auto locate = [&](int b, int64_t& B, uint32_t& addr0) {
+    while (b >= seg_prefix[seg + 1]) ++seg;
+    const int rel = b - seg_prefix[seg];
+    B = (int64_t)seg_blk0[seg] + rel;
+    addr0 = seg_addr0[seg] + (uint32_t)rel * 32u;
+  };
+  auto consume = [&](const BlockRegs<MP>& r) {
+    const float score = adc_block<MP>(r, off, lut);
+    const uint64_t key = make_key(score, r.addr0 + lane);
+    const uint64_t thr = *reinterpret_cast<volatile unsigned long long*>(cta_thr);
+    const bool live = (r.valid >> lane) & 1u;
+    if (tk.push(live && key > thr, key, lane)) {
+      if (lane == 0) atomicMax(cta_thr, (unsigned long long)tk.kth());
+    }
+  };
+
+  int b = b_begin + warp;
+  if (b < b_end) {
+    BlockRegs<MP> ra, rb;
+    int64_t B; uint32_t a0;
+    locate(b, B, a0);
+    load_block<MP>(ra, A.codes, A.valid, B, a0, lane);
+    for (;;) {
+      bool more = b + NW < b_end;
+      if (more) { locate(b + NW, B, a0); load_block<MP>(rb, A.codes, A.valid, B, a0, lane); }
+      consume(ra);
+      if (!more) break;
+      b += NW;
+      more = b + NW < b_end;
+      if (more) { locate(b + NW, B, a0); load_block<MP>(ra, A.codes, A.valid, B, a0, lane); }
+      consume(rb);
+      if (!more) break;
+      b += NW;
+    }
+  }
+  tk.flush(lane);
+  __syncthreads();
+  #pragma unroll 1
+  for (int stride = 1; stride < NW; stride <<= 1) {
+    if ((warp % (2 * stride)) == 0 && warp + stride < NW)
+      warp_merge_desc(lists + (size_t)warp * (A.kp + kTopkBuf), A.kp,
+                      lists + (size_t)(warp + stride) * (A.kp + kTopkBuf), A.kp, lane);
+    __syncthreads();
+  }
+  uint64_t* out = A.keys_out + ((size_t)q * A.S + slice) * A.k;
+  for (int i = tid; i < A.k; i += NW * 32) out[i] = lists[i];
+}
+
+// ----------------------------------------------------------------------------- merge + decode
+// keys_in: n_parts sorted lists of k keys per query -> top-k, decoded.
+// One warp per query.  (Cross-slice merge for small batches and cross-shard merge after the
+// all-gather; with n_parts == 1 it is just the decode + get_id_by_address, BaseContainer.py:58-65.)
+__global__ void __launch_bounds__(128)
+merge_topk_kernel(const uint64_t* __restrict__ keys_in, int nq, int n_parts, int k, int kp,
+                  int64_t part_stride, int64_t query_stride,
+                  const int64_t* __restrict__ address2id, int64_t capacity,
+                  float* __restrict__ values, int64_t* __restrict__ ids, int64_t* __restrict__ address,
+                  uint64_t* __restrict__ keys_out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (q >= nq) return;
+  uint64_t* A = reinterpret_cast<uint64_t*>(smem) + (size_t)warp * 2 * kp;
+  uint64_t* Bf = A + kp;
+  const uint64_t* src = keys_in + (size_t)q * query_stride;
+  for (int i = lane; i < kp; i += 32) A[i] = i < k ? src[i] : 0ull;
+  __syncwarp();
+  for (int p = 1; p < n_parts; ++p) {
+    const uint64_t* sp = src + (size_t)p * part_stride;
+    for (int i = lane; i < kp; i += 32) Bf[i] = i < k ? sp[i] : 0ull;
+    __syncwarp();
+    warp_merge_desc(A, kp, Bf, kp, lane);
+  }
+  for (int i = lane; i < k; i += 32) {
+    const uint64_t key = A[i];
+    const size_t o = (size_t)q * k + i;
+    const int64_t a = key ? (int64_t)key_addr(key) : -1;
+    if (values) values[o] = key ? key_score(key) : -INFINITY;
+    if (address) address[o] = a;
+    if (ids) ids[o] = (a >= 0 && a < capacity) ? address2id[a] : -1;
+    if (keys_out) keys_out[o] = key;
+  }
+}
+
+static int launch_merge(const uint64_t* keys_in, int nq, int n_parts, int k, int64_t part_stride, int64_t query_stride,
+                        const int64_t* address2id, int64_t capacity, float* values, int64_t* ids, int64_t* address,
+                        uint64_t* keys_out, cudaStream_t st) {
+  const int kp = next_pow2(k < 32 ? 32 : k);
+  const int wpb = 4;
+  size_t smem = (size_t)wpb * 2 * kp * 8;
+  TPQ_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_topk_kernel<<<(nq + wpb - 1) / wpb, wpb * 32, smem, st>>>(keys_in, nq, n_parts, k, kp, part_stride, query_stride,
+                                                                 address2id, capacity, values, ids, address, keys_out);
+  TPQ_LAUNCH_CHECK("merge_topk_kernel");
+  return TPQ_OK;
+}
+
+// ----------------------------------------------------------------------------- host orchestration
+constexpr int kQueryChunk = 8192;     // queries per scan launch (bounds the LUT workspace: 64 KB * MG each)
+
+static int pick_slices(int nq, int k) {
+  // enough CTAs for ~2 waves of 2 CTAs/SM when the batch is small
+  (void)k;
+  const int want = 148 * 4;
+  if (nq >= want) return 1;
+  int s = (want + nq - 1) / nq;
+  return s > 64 ? 64 : s;
+}
+
+struct SearchWs {
+  size_t coarse, probe_sims, cells, npl, xnorm, lut, keys, total;
+};
+static SearchWs search_ws(const tpq_index* ix, int nq, int n_probe, int k) {
+  SearchWs w; size_t off = 0;
+  const int MG = (ix->m_pad + 63) / 64;
+  const int chunk = nq < kQueryChunk ? nq : kQueryChunk;
+  const int S = pick_slices(nq, k);
+  w.coarse = off;     off += align_up(tpq_coarse_workspace_bytes(ix->d_vector, nq, ix->n_cells), 256);
+  w.probe_sims = off; off += align_up((size_t)nq * n_probe * 4, 256);
+  w.cells = off;      off += align_up((size_t)nq * n_probe * 8, 256);
+  w.npl = off;        off += align_up((size_t)nq * 8, 256);
+  w.xnorm = off;      off += align_up((size_t)nq * ix->d_vector * 4, 256);
+  w.lut = off;        off += align_up((size_t)chunk * MG * 65536, 256);
+  w.keys = off;       off += align_up((size_t)nq * S * k * 8, 256);
+  w.total = off;
+  return w;
+}
+
+template <int MP>
+static int launch_scan(const tpq_index* ix, const float* x, const int64_t* cells, const int64_t* npl,
+                       int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st) {
+  constexpr int NW = 8;
+  const int kp = next_pow2(k < 32 ? 32 : k);
+  ScanSmem L = scan_smem(MP, n_probe, NW, kp);
+  if (L.total > 227 * 1024) {
+    set_error("scan: M=%d n_probe=%d k=%d needs %zu B of shared memory (> 227 KB)", ix->n_subvectors, n_probe, k, L.total);
+    return TPQ_ERR_UNSUPPORTED;
+  }
+  auto kern = ivfpq_scan_kernel<MP, NW>;
+  TPQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const int MG = (MP + 63) / 64;
+  const int dsub = ix->d_vector / ix->n_subvectors;
+  for (int q0 = 0; q0 < nq; q0 += kQueryChunk) {
+    const int n = (nq - q0) < kQueryChunk ? (nq - q0) : kQueryChunk;
+    size_t xs_bytes = (size_t)(ix->d_vector + MP) * 4;
+    lut_scan_kernel<<<n, 256, xs_bytes, st>>>(x, ix->pq_codebook_t, ix->pq_norm_t, ix->d_vector, ix->n_subvectors, MP,
+                                              nq, q0, ix->metric, lut_ws);
+    TPQ_LAUNCH_CHECK("lut_scan_kernel");
+    ScanArgs A;
+    A.codes = ix->codes_scan; A.valid = ix->block_valid; A.cell_block_start = ix->cell_block_start;
+    A.cell_start = ix->cell_start; A.lut_scan = lut_ws; A.cells = cells; A.n_probe_list = npl; A.keys_out = keys;
+    A.nq = nq; A.q_base = q0; A.n_probe = n_probe; A.k = k; A.kp = kp; A.S = S;
+    kern<<<n * S, NW * 32, L.total, st>>>(A, L);
+    TPQ_LAUNCH_CHECK("ivfpq_scan_kernel");
+    (void)MG; (void)dsub;
+  }
+  return TPQ_OK;
+}
+
+static int check_index(const tpq_index* ix) {
+  TPQ_REQUIRE(ix, "null index");
+  TPQ_REQUIRE(ix->d_vector > 0 && ix->n_subvectors > 0 && ix->d_vector % ix->n_subvectors == 0,
+              "d_vector=%d must be a multiple of n_subvectors=%d", ix->d_vector, ix->n_subvectors);
+  TPQ_REQUIRE(ix->n_subvectors % 4 == 0, "n_subvectors=%d must be a multiple of 4", ix->n_subvectors);
+  TPQ_REQUIRE(ix->metric == TPQ_METRIC_EUCLIDEAN || ix->metric == TPQ_METRIC_COSINE,
+              "unsupported distance (reference supports euclidean and cosine only)");
+  TPQ_REQUIRE(ix->vq_codebook && ix->cell_start && ix->address2id, "index is missing reference buffers");
+  TPQ_REQUIRE(ix->codes_scan || ix->n_blocks == 0, "index has no scan layout (call tpq_relayout_codes first)");
+  TPQ_REQUIRE(ix->block_valid || ix->n_blocks == 0, "index has no scan layout (block_valid)");
+  TPQ_REQUIRE(ix->cell_block_start && ix->pq_codebook_t && ix->pq_norm_t, "index has no scan layout (plan / codebook)");
+  TPQ_REQUIRE(ix->m_pad == (ix->n_subvectors + 31) / 32 * 32, "index.m_pad is inconsistent");
+  TPQ_REQUIRE(ix->capacity >= 0 && ix->capacity <= 0xFFFFFFFFll, "capacity exceeds the 32-bit address range");
+  return TPQ_OK;
+}
+
+static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cells, const int64_t* npl,
+                         int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st) {
+  switch (ix->m_pad) {
+    case 32:  return launch_scan<32>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+    case 64:  return launch_scan<64>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+    case 96:  return launch_scan<96>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+    case 128: return launch_scan<128>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+    case 160: return launch_scan<160>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+    case 192: return launch_scan<192>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+    default:
+      set_error("n_subvectors=%d (padded %d) > 192 is not supported by the scan-layout path", ix->n_subvectors, ix->m_pad);
+      return TPQ_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace tpq
+
+using namespace tpq;
+
+extern "C" size_t tpq_search_workspace_bytes(const tpq_index* ix, int nq, int n_probe, int k) {
+  if (!ix || nq <= 0 || n_probe <= 0 || k <= 0) return 0;
+  return search_ws(ix, nq, n_probe, k).total;
+}
+
+extern "C" int tpq_ivfpq_search_cells(const tpq_index* ix, const float* x_dn, const int64_t* cells,
+                                      const int64_t* n_probe_list, int nq, int n_probe, int k,
+                                      float* values, int64_t* ids, int64_t* address, uint64_t* keys_out,
+                                      void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = check_index(ix)) return rc;
+  TPQ_REQUIRE(0 < k && k <= 1024, "k must be in (0, 1024], got %d", k);        // IVFPQIndex.py:473
+  TPQ_REQUIRE(nq >= 0 && n_probe >= 1, "bad n_query=%d / n_probe=%d", nq, n_probe);
+  TPQ_REQUIRE(x_dn && cells && n_probe_list, "null pointer argument");
+  if (nq == 0) return TPQ_OK;
+  SearchWs W = search_ws(ix, nq, n_probe, k);
+  if (!ws || ws_bytes < W.total) { set_error("workspace too small (%zu < %zu)", ws_bytes, W.total); return TPQ_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+  const int S = pick_slices(nq, k);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(w + W.keys);
+  if (int rc = scan_dispatch(ix, x_dn, cells, n_probe_list, nq, n_probe, k, S,
+                             reinterpret_cast<float*>(w + W.lut), keys, st)) return rc;
+  return launch_merge(keys, nq, S, k, k, (int64_t)S * k, ix->address2id, ix->capacity, values, ids, address, keys_out, st);
+}
+
+extern "C" int tpq_ivfpq_search(const tpq_index* ix, const float* x_dn, int nq, int n_probe, int k,
+                                int smart, float temperature,
+                                float* values, int64_t* ids, int64_t* address, uint64_t* keys_out,
+                                void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = check_index(ix)) return rc;
+  TPQ_REQUIRE(0 < k && k <= 1024, "k must be in (0, 1024], got %d", k);
+  TPQ_REQUIRE(nq >= 0 && x_dn, "bad query batch");
+  TPQ_REQUIRE(n_probe >= 1 && n_probe <= ix->n_cells, "n_probe=%d must be in [1, n_cells=%d]", n_probe, ix->n_cells);
+  if (nq == 0) return TPQ_OK;
+  SearchWs W = search_ws(ix, nq, n_probe, k);
+  if (!ws || ws_bytes < W.total) { set_error("workspace too small (%zu < %zu)", ws_bytes, W.total); return TPQ_ERR_WORKSPACE; }
+  uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+  const float* x = x_dn;
+  if (ix->metric == TPQ_METRIC_COSINE) {                                        // IVFPQIndex.py:474-475
+    float* xn = reinterpret_cast<float*>(w + W.xnorm);
+    if (int rc = tpq_normalize_columns(x_dn, ix->d_vector, nq, xn, stream)) return rc;
+    x = xn;
+  }
+  float* probe_sims = reinterpret_cast<float*>(w + W.probe_sims);
+  int64_t* cells = reinterpret_cast<int64_t*>(w + W.cells);
+  int64_t* npl = reinterpret_cast<int64_t*>(w + W.npl);
+  if (int rc = tpq_coarse_probe(x, ix->vq_codebook, ix->d_vector, nq, ix->n_cells, n_probe, smart, temperature,
+                                probe_sims, cells, npl, w + W.coarse, W.probe_sims - W.coarse, stream)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = pick_slices(nq, k);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(w + W.keys);
+  if (int rc = scan_dispatch(ix, x, cells, npl, nq, n_probe, k, S, reinterpret_cast<float*>(w + W.lut), keys, st)) return rc;
+  return launch_merge(keys, nq, S, k, k, (int64_t)S * k, ix->address2id, ix->capacity, values, ids, address, keys_out, st);
+}
+
+extern "C" int tpq_merge_topk(const uint64_t* keys_in, int nq, int n_parts, int k,
+                              const int64_t* address2id, int64_t capacity,
+                              float* values, int64_t* ids, int64_t* address, void* stream) {
+  TPQ_REQUIRE(keys_in && nq >= 0 && n_parts >= 1 && 0 < k && k <= 1024, "tpq_merge_topk: bad argument");
+  TPQ_REQUIRE(!ids || address2id, "tpq_merge_topk: ids requested without address2id");
+  if (nq == 0) return TPQ_OK;
+  // keys_in is [n_parts, nq, k] (the all-gather's natural layout): part stride nq*k, query stride k
+  return launch_merge(keys_in, nq, n_parts, k, (int64_t)nq * k, k, address2id, capacity, values, ids, address, nullptr,
+                      (cudaStream_t)stream);
+}

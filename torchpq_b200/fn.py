@@ -1,0 +1,105 @@
+"""Operator-level mirrors of the reference's fused ops (same names, argument meaning and checks).
+
+    IVFPQTopk.topk       torchpq/fn/IVFPQTopk.py:54-104 -> kernels/IVFPQTopkCuda.py:81-142
+    precompute_adc       torchpq/codec/PQCodec.py:62-75
+    coarse_probe         torchpq/metric.py:74-94 + fn/Topk.py:43-67 + index/IVFPQIndex.py:499-512
+    normalize            torchpq/util.py:38-43
+Each is one call into the sm_100a library; tensors are passed as raw device pointers.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr
+
+
+def _cuda_f32(t, name):
+    assert t.device.type == "cuda", f"{name} must be a CUDA tensor (torchpq_b200 has no CPU path)"
+    assert t.dtype == torch.float32, f"{name} must be float32"
+    return t.contiguous()
+
+
+def normalize(x, dim=0):
+    """util.normalize for a [d, n] matrix along dim 0: x / (||x|| + 1e-9)."""
+    assert dim == 0 and x.dim() == 2
+    x = _cuda_f32(x, "x")
+    out = torch.empty_like(x)
+    check(lib.tpq_normalize_columns(ptr(x), x.shape[0], x.shape[1], ptr(out), _lib.current_stream(x.device)))
+    return out
+
+
+def coarse_probe(x, vq_codebook, n_probe, use_smart_probing=True, smart_probing_temperature=30.0):
+    """x [d, nq], vq_codebook [d, n_cells] -> (topk_sims [nq, n_probe] desc, cells [nq, n_probe] i64,
+    n_probe_list [nq] i64)."""
+    x, cb = _cuda_f32(x, "x"), _cuda_f32(vq_codebook, "vq_codebook")
+    d, nq = x.shape
+    assert cb.shape[0] == d
+    n_cells = cb.shape[1]
+    dev = x.device
+    sims = torch.empty(nq, n_probe, dtype=torch.float32, device=dev)
+    cells = torch.empty(nq, n_probe, dtype=torch.long, device=dev)
+    npl = torch.empty(nq, dtype=torch.long, device=dev)
+    ws_bytes = lib.tpq_coarse_workspace_bytes(d, nq, n_cells)
+    ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
+    check(lib.tpq_coarse_probe(ptr(x), ptr(cb), d, nq, n_cells, int(n_probe), int(bool(use_smart_probing)),
+                               float(smart_probing_temperature), ptr(sims), ptr(cells), ptr(npl),
+                               ptr(ws), ws_bytes, _lib.current_stream(dev)))
+    return sims, cells, npl
+
+
+def precompute_adc(query, pq_codebook, distance="euclidean"):
+    """PQCodec.precompute_adc: query [d, nq], pq_codebook [M, dsub, 256] -> [M, nq, 256] fp32."""
+    q, cb = _cuda_f32(query, "query"), _cuda_f32(pq_codebook, "pq_codebook")
+    M, dsub, K = cb.shape
+    assert K == 256 and q.shape[0] == M * dsub                           # PQCodec.py:71
+    nq = q.shape[1]
+    out = torch.empty(M, nq, 256, dtype=torch.float32, device=q.device)
+    check(lib.tpq_build_lut(ptr(q), ptr(cb), M * dsub, M, nq, _lib.METRIC[distance], ptr(out),
+                            _lib.current_stream(q.device)))
+    return out
+
+
+class IVFPQTopk:
+    """fn.IVFPQTopk (fn/IVFPQTopk.py:8-52): fused ADC scan + top-k over the reference storage layout."""
+
+    def __init__(self, n_subvectors, contiguous_size=4, sm_size=None):
+        assert contiguous_size == 4
+        self.n_subvectors = n_subvectors
+
+    def topk(self, data, precomputed, cell_start, cell_size, is_empty, n_probe_list, k=256):
+        assert 0 < k <= 1024                                             # fn/IVFPQTopk.py:64
+        n_data = data.shape[1]
+        n_query, n_probe = cell_start.shape
+        # IVFPQTopkCuda.py:98-110
+        assert precomputed.shape == (self.n_subvectors, n_query, 256)
+        assert data.shape[0] == self.n_subvectors // 4 and data.shape[2] == 4
+        assert is_empty.shape[0] == n_data
+        assert cell_size.shape[1] == n_probe
+        assert data.dtype == torch.uint8 and precomputed.dtype == torch.float32
+        assert cell_start.dtype == cell_size.dtype == torch.int64
+        assert is_empty.dtype == torch.uint8
+        assert n_probe_list.shape == (n_query,) and n_probe_list.dtype == torch.int64
+        dev = data.device
+        assert dev.type == "cuda"
+        data, precomputed, is_empty = data.contiguous(), precomputed.contiguous(), is_empty.contiguous()
+        cell_start, cell_size, n_probe_list = cell_start.contiguous(), cell_size.contiguous(), n_probe_list.contiguous()
+        values = torch.empty(n_query, k, dtype=torch.float32, device=dev)
+        address = torch.empty(n_query, k, dtype=torch.int64, device=dev)
+        check(lib.tpq_ivfpq_topk(ptr(data), ptr(precomputed), ptr(is_empty), ptr(cell_start), ptr(cell_size),
+                                 ptr(n_probe_list), n_data, self.n_subvectors, n_query, n_probe, k,
+                                 ptr(values), ptr(address), None, 0, _lib.current_stream(dev)))
+        return values, address
+
+
+def merge_topk(keys, address2id):
+    """keys [n_parts, nq, k] int64-viewed packed candidates (each part sorted) -> (values, ids, address)."""
+    assert keys.dim() == 3 and keys.dtype == torch.int64 and keys.is_contiguous()
+    n_parts, nq, k = keys.shape
+    dev = keys.device
+    values = torch.empty(nq, k, dtype=torch.float32, device=dev)
+    ids = torch.empty(nq, k, dtype=torch.long, device=dev)
+    address = torch.empty(nq, k, dtype=torch.long, device=dev)
+    check(lib.tpq_merge_topk(ptr(keys), nq, n_parts, k, ptr(address2id), address2id.shape[0],
+                             ptr(values), ptr(ids), ptr(address), _lib.current_stream(dev)))
+    return values, ids, address

@@ -1,0 +1,233 @@
+"""Host-side mirror of ``torchpq.index.IVFPQIndex`` for the search hot path.
+
+Same constructor arguments, attributes, registered buffers (so checkpoints interchange)
+and ``search`` / ``search_cells`` signatures and return values as the reference class
+(torchpq/index/IVFPQIndex.py:12-87, 407-524; container/CellContainer.py:46-81;
+container/BaseContainer.py:32-38).  All computation is the sm_100a library behind
+``include/tpq_b200.h``; PyTorch is used for device memory and streams only.
+
+Not covered (out of the hot-path scope): residual PQ
+(``pq_use_residual=True``), ``use_cublas=False`` / tensor-core coarse variants.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr
+from .modules import StateModule, Codec
+
+
+def _fingerprint(*tensors):
+    return tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None for t in tensors)
+
+
+class ScanLayout:
+    """The scan ("shadow") layout of one index (or of one shard of it) + its ``tpq_index`` struct.
+
+    Built from the reference buffers by ``tpq_relayout_*``; rebuilt whenever any of those
+    buffers is replaced or modified in place (``add``, ``expand``, ``load_state_dict``...)."""
+
+    def __init__(self, index: "IVFPQIndex", shard_rank: int = 0, shard_world: int = 1):
+        dev = index._storage.device
+        assert dev.type == "cuda", "torchpq_b200 has no CPU path: the index must live on a CUDA device"
+        stream = _lib.current_stream(dev)
+        M, d, Cn = index.n_subvectors, index.d_vector, index.n_cells
+        self.m_pad = (M + 31) // 32 * 32
+        self.keep = (index._storage, index._is_empty, index._cell_start, index._cell_size, index._address2id,
+                     index.vq_codec.codebook, index.pq_codec.codebook)
+        for t in self.keep:
+            assert t is not None and t.is_contiguous()
+        self.cell_block_start = torch.empty(Cn + 1, dtype=torch.int32, device=dev)
+        check(lib.tpq_relayout_plan(ptr(index._cell_size), Cn, shard_rank, shard_world,
+                                    ptr(self.cell_block_start), stream))
+        self.n_blocks = int(self.cell_block_start[Cn].item())          # one host sync per (re)build
+        self.codes_scan = torch.empty(max(1, lib.tpq_codes_scan_bytes(M, self.n_blocks)), dtype=torch.uint8, device=dev)
+        self.block_valid = torch.empty(max(1, self.n_blocks), dtype=torch.int32, device=dev)
+        self.pq_codebook_t = torch.empty(256 * self.m_pad * (d // M), dtype=torch.float32, device=dev)
+        self.pq_norm_t = torch.empty(256 * self.m_pad, dtype=torch.float32, device=dev)
+        ix = _lib.TpqIndex()
+        ix.d_vector, ix.n_subvectors, ix.n_cells = d, M, Cn
+        ix.metric = _lib.METRIC[index.distance]
+        ix.capacity = index._address2id.shape[0]
+        ix.vq_codebook = index.vq_codec.codebook.data_ptr()
+        ix.pq_codebook = index.pq_codec.codebook.data_ptr()
+        ix.storage = index._storage.data_ptr()
+        ix.is_empty = index._is_empty.data_ptr()
+        ix.cell_start = index._cell_start.data_ptr()
+        ix.cell_size = index._cell_size.data_ptr()
+        ix.address2id = index._address2id.data_ptr()
+        ix.m_pad, ix.shard_rank, ix.shard_world = self.m_pad, shard_rank, shard_world
+        ix.n_blocks = self.n_blocks
+        ix.codes_scan = self.codes_scan.data_ptr()
+        ix.block_valid = self.block_valid.data_ptr()
+        ix.cell_block_start = self.cell_block_start.data_ptr()
+        ix.pq_codebook_t = self.pq_codebook_t.data_ptr()
+        ix.pq_norm_t = self.pq_norm_t.data_ptr()
+        self.cindex = ix
+        check(lib.tpq_relayout_codes(C.byref(ix), ptr(self.codes_scan), ptr(self.block_valid), stream))
+        check(lib.tpq_relayout_codebook(ptr(index.pq_codec.codebook), d, M, ix.metric,
+                                        ptr(self.pq_codebook_t), ptr(self.pq_norm_t), stream))
+        self.fingerprint = _fingerprint(*self.keep)
+
+
+class IVFPQIndex(StateModule):
+    def __init__(self, d_vector, n_subvectors=8, n_cells=128, initial_size=None, expand_step_size=128,
+                 expand_mode="double", distance="euclidean", device="cuda:0", pq_use_residual=False, verbose=0):
+        super().__init__()
+        assert d_vector % n_subvectors == 0                              # IVFPQIndex.py:30
+        assert n_subvectors % 4 == 0, "code_size % contiguous_size(4) == 0"   # CellContainer.py:36, IVFPQIndex.py:41
+        assert expand_mode in ("step", "double") and expand_step_size > 0      # BaseContainer.py:19-21
+        assert distance in ("euclidean", "cosine"), \
+            "the reference can only build/search euclidean and cosine IVFPQ indexes (MultiKMeans.py:82-115,218-223)"
+        if pq_use_residual:
+            raise NotImplementedError("pq_use_residual=True (residual IVFPQ) is outside the ported hot path")
+        if initial_size is None:
+            initial_size = expand_step_size                              # CellContainer.py:23-24
+        assert initial_size >= 0 and n_cells > 0
+        self.d_vector, self.n_subvectors, self.d_subvector = d_vector, n_subvectors, d_vector // n_subvectors
+        self.n_cells, self.code_size, self.contiguous_size = n_cells, n_subvectors, 4
+        self.distance, self.device, self.verbose = distance, device, verbose
+        self.initial_size, self.expand_step_size, self.expand_mode = initial_size, expand_step_size, expand_mode
+        self.pq_use_residual = False
+        self.n_probe = 1                                                 # IVFPQIndex.py:51
+        self.use_smart_probing = True                                    # IVFPQIndex.py:58
+        self.smart_probing_temperature = 30.0                            # IVFPQIndex.py:59
+        self._max_id = -1
+        dev = torch.device(device)
+        cap = n_cells * initial_size
+        self.register_buffer("_address2id", -torch.ones(cap, dtype=torch.long, device=dev))
+        self.register_buffer("_id2address", None)
+        self.register_buffer("_storage", torch.zeros(n_subvectors // 4, cap, 4, dtype=torch.uint8, device=dev))
+        self.register_buffer("_cell_start", torch.arange(n_cells, device=dev) * initial_size)
+        self.register_buffer("_cell_size", torch.zeros(n_cells, dtype=torch.long, device=dev))
+        self.register_buffer("_cell_capacity", torch.zeros(n_cells, dtype=torch.long, device=dev) + initial_size)
+        self.register_buffer("_is_empty", torch.ones(cap, dtype=torch.uint8, device=dev))
+        self.vq_codec = Codec()
+        self.pq_codec = Codec()
+        self._layout: Optional[ScanLayout] = None
+        self._shard = (0, 1)
+
+    # ------------------------------------------------------------------ container properties
+    @property
+    def capacity(self):
+        return self._address2id.shape[0]
+
+    @property
+    def max_id(self):
+        return self._max_id
+
+    @property
+    def n_items(self):
+        return int(self._cell_size.sum().item())
+
+    # flags the reference exposes and this path ignores (always the fused fp32 coarse kernel)
+    use_cublas = True
+    use_tensor_core = False
+    fp16_scale_mode = "a"
+
+    def _state_changed(self):
+        self._layout = None
+
+    # ------------------------------------------------------------------ state import
+    def load_state(self, st):
+        """Adopt an ``oracle.ivfpq_oracle.IndexState``-shaped object (numpy buffers) -- test/bench helper."""
+        dev = torch.device(self.device)
+
+        def T(a):
+            return torch.as_tensor(a).to(dev).contiguous()
+
+        assert (st.d_vector, st.n_subvectors, st.n_cells, st.distance) == \
+               (self.d_vector, self.n_subvectors, self.n_cells, self.distance)
+        for name, val in (("_storage", st.storage), ("_is_empty", st.is_empty), ("_cell_start", st.cell_start),
+                          ("_cell_size", st.cell_size), ("_cell_capacity", st.cell_capacity),
+                          ("_address2id", st.address2id)):
+            delattr(self, name)
+            self.register_buffer(name, T(val))
+        self.vq_codec.set_codebook(T(st.vq_codebook))
+        self.pq_codec.set_codebook(T(st.pq_codebook))
+        self._max_id = int(st.max_id)
+        self.n_probe = st.n_probe
+        self.use_smart_probing = st.use_smart_probing
+        self.smart_probing_temperature = st.smart_probing_temperature
+        self._layout = None
+        return self
+
+    def set_shard(self, rank: int, world: int):
+        """Scan only the cells c with c % world == rank (cell-sharded multi-GPU search, dist.py)."""
+        assert 0 <= rank < world
+        if (rank, world) != self._shard:
+            self._shard = (rank, world)
+            self._layout = None
+
+    def layout(self) -> ScanLayout:
+        fp = _fingerprint(self._storage, self._is_empty, self._cell_start, self._cell_size, self._address2id,
+                          self.vq_codec.codebook, self.pq_codec.codebook)
+        if self._layout is None or self._layout.fingerprint != fp:
+            assert self.vq_codec.is_trained and self.pq_codec.is_trained, "codec is not trained"
+            self._layout = ScanLayout(self, *self._shard)
+        return self._layout
+
+    # ------------------------------------------------------------------ search
+    def _check_query(self, x, k):
+        assert len(x.shape) == 2                                          # IVFPQIndex.py:471
+        assert x.shape[0] == self.d_vector                                # :472
+        assert 0 < k <= 1024                                              # :473
+        assert x.dtype == torch.float32 and x.device == self._storage.device
+        return x.contiguous()
+
+    def search(self, x, k=1, return_address=False, return_keys=False):
+        """IVFPQIndex.search (IVFPQIndex.py:469-524): x [d_vector, n_query] fp32 on the index device
+        -> (topk_values [n_query, k] fp32 descending, topk_ids [n_query, k] int64[, topk_address])."""
+        x = self._check_query(x, k)
+        lay = self.layout()
+        dev, nq = x.device, x.shape[1]
+        values = torch.empty(nq, k, dtype=torch.float32, device=dev)
+        ids = torch.empty(nq, k, dtype=torch.long, device=dev)
+        address = torch.empty(nq, k, dtype=torch.long, device=dev) if return_address else None
+        keys = torch.empty(nq, k, dtype=torch.int64, device=dev) if return_keys else None
+        n_probe = int(self.n_probe)
+        ws_bytes = lib.tpq_search_workspace_bytes(C.byref(lay.cindex), nq, n_probe, k)
+        ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
+        check(lib.tpq_ivfpq_search(C.byref(lay.cindex), ptr(x), nq, n_probe, k,
+                                   int(bool(self.use_smart_probing)), float(self.smart_probing_temperature),
+                                   ptr(values), ptr(ids), ptr(address), ptr(keys), ptr(ws), ws_bytes,
+                                   _lib.current_stream(dev)))
+        out = (values, ids)
+        if return_address:
+            out = out + (address,)
+        if return_keys:
+            out = out + (keys,)
+        return out
+
+    def search_cells(self, x, cells, base_sims=None, n_probe_list=None, k=1, return_address=False):
+        """IVFPQIndex.search_cells, non-residual branch (IVFPQIndex.py:407-467)."""
+        x = self._check_query(x, k)
+        lay = self.layout()
+        dev, nq = x.device, x.shape[1]
+        assert cells.dtype == torch.int64 and cells.shape[0] == nq and cells.dim() == 2
+        n_probe = cells.shape[1]
+        if n_probe_list is None:
+            n_probe_list = torch.zeros(nq, dtype=torch.long, device=dev) + n_probe
+        assert n_probe_list.shape == (nq,) and n_probe_list.dtype == torch.int64     # IVFPQTopkCuda.py:109-110
+        cells, n_probe_list = cells.contiguous(), n_probe_list.contiguous()
+        values = torch.empty(nq, k, dtype=torch.float32, device=dev)
+        ids = torch.empty(nq, k, dtype=torch.long, device=dev)
+        address = torch.empty(nq, k, dtype=torch.long, device=dev) if return_address else None
+        ws_bytes = lib.tpq_search_workspace_bytes(C.byref(lay.cindex), nq, n_probe, k)
+        ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
+        check(lib.tpq_ivfpq_search_cells(C.byref(lay.cindex), ptr(x), ptr(cells), ptr(n_probe_list), nq, n_probe, k,
+                                         ptr(values), ptr(ids), ptr(address), None, ptr(ws), ws_bytes,
+                                         _lib.current_stream(dev)))
+        return (values, ids, address) if return_address else (values, ids)
+
+    def get_id_by_address(self, address):
+        """BaseContainer.get_id_by_address (BaseContainer.py:58-65) -- plain tensor indexing, not on the hot path."""
+        assert address.dtype == torch.int64
+        mask = (0 <= address) & (address < self.capacity)
+        ids = torch.ones_like(address) * -1
+        ids[mask] = self._address2id[address[mask]]
+        return ids
