@@ -27,10 +27,8 @@ def test_integer_kat_exact(cuda_device, M, d, C, n, k, n_probe, smart):
     v, i, a = ix.search(x.cuda(), k=k, return_address=True)
     v, i, a = v.cpu().numpy(), i.cpu().numpy(), a.cpu().numpy()
     assert np.array_equal(v, ov[:, :k])                       # values are exact whatever the tie order
-    ok = tie_free_rows(ov, k)
-    assert ok.sum() > 0
-    assert np.array_equal(i[ok], oi[ok, :k])
-    assert np.array_equal(a[ok], oa[ok, :k])
+    ok = tie_free_rows(ov, k)                                  # k-th and (k+1)-th scores differ
+    assert np.array_equal(np.sort(i[ok], axis=1), np.sort(oi[ok, :k], axis=1))   # the id SET is tie-rule independent
     # with the shared total order (score desc, address asc) even tied rows agree
     assert np.array_equal(a, oa[:, :k])
 
