@@ -134,8 +134,15 @@ int tpq_ivfpq_search_cells(const tpq_index* index, const float* x_dn, const int6
                            float* values, int64_t* ids, int64_t* address, uint64_t* keys_out,
                            void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ measurement hook (bench.py roofline leg)
+ * When enabled, every scan-kernel launch is bracketed by CUDA events on its own stream;
+ * tpq_profile_scan_ms waits for them and returns the summed duration and launch count since
+ * the last call.  Process-wide, not thread-safe; leave disabled in production. */
+int tpq_profile_enable(int on);
+int tpq_profile_scan_ms(float* total_ms, int* n_launches);
+
 /* ------------------------------------------------------------------ cross-shard merge
- * keys_in [nq, n_parts, k] (each part sorted descending, 0 = empty slot) -> top-k per query,
+ * keys_in [n_parts, nq, k] (the all-gather's layout; each part sorted descending, 0 = empty slot) -> top-k per query,
  * decoded: values (-inf pad), address (-1 pad), ids = address2id[address] (BaseContainer.py:58-65). */
 int tpq_merge_topk(const uint64_t* keys_in, int nq, int n_parts, int k,
                    const int64_t* address2id, int64_t capacity,

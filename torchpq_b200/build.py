@@ -1,0 +1,163 @@
+"""Index build side (train / encode / add) -- the callers *before* the search hot path.
+
+SURVEY.md section 8(f) rank 1-2 ("next" rows).  This first version expresses the reference's
+semantics with plain PyTorch tensor ops on the index device so that large synthetic indexes
+can be built on the GPU for the search benchmark; it is NOT the measured path and uses no
+custom kernels yet.  Semantics followed:
+
+    IVFPQIndex.train        torchpq/index/IVFPQIndex.py:234-260  (VQ: <=15 Lloyd iters, PQ: <=25)
+    KMeans / MultiKMeans    torchpq/clustering/KMeans.py:399-438, MultiKMeans.py:415-453
+        assignment = arg-max of negative squared L2 (kernels/cuda/max_sim.cu:78-98)
+        update     = member mean, empty cluster -> 0 (kernels/cuda/compute_centroids.cu:9-86)
+    IVFPQIndex.add          torchpq/index/IVFPQIndex.py:316-364
+    CellContainer.add       torchpq/container/CellContainer.py:313-367 (ioa, expand loop, write address
+                            = ioa-th empty slot of the cell, get_write_address_v2.cu:9-41)
+Unlike the reference (unseeded np.random.choice, MultiKMeans.py:277-283) initial centroids come
+from a seeded torch.Generator, so training is reproducible.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def _assign(data: torch.Tensor, cent: torch.Tensor, budget: int = 1 << 30) -> torch.Tensor:
+    """data [l, d, n], cent [l, d, k] -> labels [l, n] int64 (arg-max of -|x-c|^2; |x|^2 is constant per row)."""
+    l, d, n = data.shape
+    out = torch.empty(l, n, dtype=torch.long, device=data.device)
+    c2 = (cent ** 2).sum(dim=1)                                  # [l, k]
+    per = max(1, budget // max(1, l * cent.shape[2]))             # <= `budget` similarity entries at a time
+    for s in range(0, n, per):
+        a = data[:, :, s:s + per]
+        sim = torch.baddbmm(-c2[:, None, :], a.transpose(1, 2), cent, alpha=2.0)   # [l, m, k]
+        out[:, s:s + per] = sim.argmax(dim=2)
+    return out
+
+
+def multi_kmeans(data: torch.Tensor, k: int, max_iter: int, tol: float = 1e-4, seed: int = 0) -> torch.Tensor:
+    """l independent k-means over data [l, d, n] -> centroids [l, d, k]."""
+    l, d, n = data.shape
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    pick = torch.randperm(n, generator=gen)[:k].to(data.device)
+    cent = data[:, :, pick].clone()
+    if cent.shape[2] < k:
+        cent = torch.cat([cent, torch.zeros(l, d, k - cent.shape[2], device=data.device)], dim=2)
+    ones = torch.ones(l, n, device=data.device)
+    for _ in range(max_iter):
+        lab = _assign(data, cent)
+        sums = torch.zeros(l, d, k, device=data.device).scatter_add_(2, lab[:, None, :].expand(l, d, n), data)
+        cnt = torch.zeros(l, k, device=data.device).scatter_add_(1, lab, ones)
+        new = torch.where(cnt[:, None, :] > 0, sums / cnt.clamp(min=1)[:, None, :], torch.zeros((), device=data.device))
+        shift = (new - cent).pow(2).sum(dim=1).sqrt().mean()
+        cent = new
+        if float(shift) < tol:
+            break
+    return cent
+
+
+def train(index, x: torch.Tensor, seed: int = 0, vq_iters: int = 15, pq_iters: int = 25):
+    """IVFPQIndex.train: fit the coarse quantizer and the M sub-quantizers on x [d, n]."""
+    assert x.dim() == 2 and x.shape[0] == index.d_vector
+    from . import fn
+    if index.distance == "cosine":
+        x = fn.normalize(x.contiguous())
+    vq = multi_kmeans(x[None].contiguous(), index.n_cells, vq_iters, seed=seed)[0].contiguous()
+    sub = x.reshape(index.n_subvectors, index.d_subvector, x.shape[1]).contiguous()
+    pq = multi_kmeans(sub, 256, pq_iters, seed=seed + 1).contiguous()
+    index.vq_codec.set_codebook(vq)
+    index.pq_codec.set_codebook(pq)
+    index._state_changed()
+
+
+def encode(index, x: torch.Tensor):
+    """-> (cells [n] i64, codes [M, n] u8) for x [d, n] (already normalised for cosine)."""
+    cells = _assign(x[None], index.vq_codec.codebook[None])[0]
+    sub = x.reshape(index.n_subvectors, index.d_subvector, x.shape[1])
+    codes = _assign(sub, index.pq_codec.codebook).to(torch.uint8)
+    return cells, codes
+
+
+def _ioa(cells: torch.Tensor) -> torch.Tensor:
+    """index of appearance of each label among equal labels, input order (get_ioa.cu:8-47)."""
+    n = cells.shape[0]
+    order = torch.sort(cells, stable=True).indices
+    sc = cells[order]
+    first = torch.ones(n, dtype=torch.bool, device=cells.device)
+    first[1:] = sc[1:] != sc[:-1]
+    ar = torch.arange(n, device=cells.device)
+    run_start = torch.cummax(torch.where(first, ar, torch.zeros_like(ar)), 0).values
+    ioa = torch.empty(n, dtype=torch.long, device=cells.device)
+    ioa[order] = ar - run_start
+    return ioa
+
+
+def _expand(index, cells: torch.Tensor):
+    """CellContainer.expand (CellContainer.py:249-311), one rebuild for all listed cells."""
+    dev = index._storage.device
+    grow = torch.zeros(index.n_cells, dtype=torch.long, device=dev)
+    grow[cells] = index._cell_capacity[cells] if index.expand_mode == "double" else index.expand_step_size
+    shift = torch.cumsum(grow, 0) - grow                           # slots inserted before each cell
+    old_start, old_cap = index._cell_start, index._cell_capacity
+    new_capacity_total = index.capacity + int(grow.sum().item())
+    # old address -> new address
+    adr = torch.arange(index.capacity, device=dev)
+    cell_of = torch.searchsorted(old_start, adr, right=True) - 1
+    new_adr = adr + shift[cell_of]
+    storage = torch.zeros(index._storage.shape[0], new_capacity_total, 4, dtype=torch.uint8, device=dev)
+    storage[:, new_adr] = index._storage
+    a2i = -torch.ones(new_capacity_total, dtype=torch.long, device=dev)
+    a2i[new_adr] = index._address2id
+    emp = torch.ones(new_capacity_total, dtype=torch.uint8, device=dev)
+    emp[new_adr] = index._is_empty
+    for name, val in (("_storage", storage), ("_address2id", a2i), ("_is_empty", emp)):
+        delattr(index, name)
+        index.register_buffer(name, val)
+    index._cell_start += shift
+    index._cell_capacity += grow
+
+
+def container_add(index, codes: torch.Tensor, cells: torch.Tensor, ids=None, return_address=False):
+    """CellContainer.add (CellContainer.py:313-367)."""
+    assert codes.dtype == torch.uint8 and cells.dtype == torch.long
+    assert codes.shape[0] == index.code_size and codes.shape[1] == cells.shape[0]
+    dev = index._storage.device
+    n = cells.shape[0]
+    if ids is None:
+        ids = torch.arange(n, device=dev, dtype=torch.long) + index.max_id + 1
+    else:
+        assert ids.dtype == torch.long and ids.shape[0] == n
+        ids = ids.to(dev)
+    ioa = _ioa(cells)
+    while True:
+        free = index._cell_capacity[cells] - index._cell_size[cells] - (ioa + 1)
+        need = cells[free < 0].unique()
+        if need.shape[0] == 0:
+            break
+        _expand(index, need)
+    empty_adr = torch.nonzero(index._is_empty == 1)[:, 0]           # sorted
+    first_empty = torch.searchsorted(empty_adr, index._cell_start)   # index of each cell's first empty slot
+    write = empty_adr[first_empty[cells] + ioa]
+    M = index.code_size
+    index._storage[:, write] = codes.reshape(M // 4, 4, n).transpose(1, 2)
+    index._address2id[write] = ids
+    if n:
+        index._max_id = max(index._max_id, int(ids.max().item()))
+    index._is_empty[write] = 0
+    uc, cnt = cells.unique(return_counts=True)
+    index._cell_size[uc] += cnt
+    index._state_changed()
+    return (ids, write) if return_address else ids
+
+
+def add(index, x: torch.Tensor, ids=None, return_address=False, chunk: int = 1 << 20):
+    """IVFPQIndex.add: encode x [d, n] and store it."""
+    assert x.dim() == 2 and x.shape[0] == index.d_vector
+    from . import fn
+    cells_l, codes_l = [], []
+    for s in range(0, x.shape[1], chunk):
+        xc = x[:, s:s + chunk].contiguous()
+        if index.distance == "cosine":
+            xc = fn.normalize(xc)
+        c, q = encode(index, xc)
+        cells_l.append(c)
+        codes_l.append(q)
+    return container_add(index, torch.cat(codes_l, 1), torch.cat(cells_l, 0), ids, return_address)

@@ -307,7 +307,14 @@ static int launch_merge(const uint64_t* keys_in, int nq, int n_parts, int k, int
 }
 
 // ----------------------------------------------------------------------------- host orchestration
-constexpr int kQueryChunk = 8192;     // queries per scan launch (bounds the LUT workspace: 64 KB * MG each)
+constexpr int kQueryChunk = 16384;    // queries per scan launch (bounds the LUT workspace: 64 KB * MG each)
+
+// optional CUDA-event timing of the scan launches (bench.py's roofline leg); off by default
+constexpr int kProfMax = 64;
+static bool g_prof_on = false;
+static int g_prof_n = 0;
+static cudaEvent_t g_prof_start[kProfMax], g_prof_stop[kProfMax];
+static bool g_prof_created = false;
 
 static int pick_slices(int nq, int k) {
   // enough CTAs for ~2 waves of 2 CTAs/SM when the batch is small
@@ -361,7 +368,10 @@ static int launch_scan(const tpq_index* ix, const float* x, const int64_t* cells
     A.codes = ix->codes_scan; A.valid = ix->block_valid; A.cell_block_start = ix->cell_block_start;
     A.cell_start = ix->cell_start; A.lut_scan = lut_ws; A.cells = cells; A.n_probe_list = npl; A.keys_out = keys;
     A.nq = nq; A.q_base = q0; A.n_probe = n_probe; A.k = k; A.kp = kp; A.S = S;
+    const bool prof = g_prof_on && g_prof_n < kProfMax;
+    if (prof) cudaEventRecord(g_prof_start[g_prof_n], st);
     kern<<<n * S, NW * 32, L.total, st>>>(A, L);
+    if (prof) cudaEventRecord(g_prof_stop[g_prof_n++], st);
     TPQ_LAUNCH_CHECK("ivfpq_scan_kernel");
     (void)MG; (void)dsub;
   }
@@ -402,6 +412,30 @@ static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cel
 }  // namespace tpq
 
 using namespace tpq;
+
+extern "C" int tpq_profile_enable(int on) {
+  if (on && !g_prof_created) {
+    for (int i = 0; i < kProfMax; ++i) { TPQ_CUDA(cudaEventCreate(&g_prof_start[i])); TPQ_CUDA(cudaEventCreate(&g_prof_stop[i])); }
+    g_prof_created = true;
+  }
+  g_prof_on = on != 0;
+  g_prof_n = 0;
+  return TPQ_OK;
+}
+
+extern "C" int tpq_profile_scan_ms(float* total_ms, int* n_launches) {
+  TPQ_REQUIRE(total_ms && n_launches, "null pointer");
+  float tot = 0.f;
+  for (int i = 0; i < g_prof_n; ++i) {
+    TPQ_CUDA(cudaEventSynchronize(g_prof_stop[i]));
+    float ms = 0.f;
+    TPQ_CUDA(cudaEventElapsedTime(&ms, g_prof_start[i], g_prof_stop[i]));
+    tot += ms;
+  }
+  *total_ms = tot; *n_launches = g_prof_n;
+  g_prof_n = 0;
+  return TPQ_OK;
+}
 
 extern "C" size_t tpq_search_workspace_bytes(const tpq_index* ix, int nq, int n_probe, int k) {
   if (!ix || nq <= 0 || n_probe <= 0 || k <= 0) return 0;

@@ -1,0 +1,66 @@
+"""Cell-sharded multi-GPU search: one process per GPU, one NCCL all-gather per query batch.
+
+The reference is single-GPU only (no NCCL / torch.distributed anywhere).
+Partitioning: rank r scans the cells c with c % world == r; the two small
+codebooks and the address->id table are replicated; every rank sees the full query batch, runs
+the (deterministic, identical) coarse probe redundantly, scans only its own cells and emits its
+local top-k as packed 64-bit (score, address) keys.  One ``all_gather_into_tensor`` of
+[nq, k] keys (8 B per candidate) follows, then the same merge kernel that combines CTA slices
+picks the global top-k -- the union of per-shard top-k's contains the global top-k, and keys
+carry GLOBAL addresses, so sharded == unsharded bit for bit, ties included.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import fn
+
+
+def merge_gathered(keys_all: torch.Tensor, address2id: torch.Tensor):
+    """keys_all [world, nq, k] -> (values, ids, address); CUDA kernel tpq_merge_topk."""
+    return fn.merge_topk(keys_all.contiguous(), address2id)
+
+
+def sharded_search(index, x: torch.Tensor, k: int, group=None, return_address: bool = False):
+    """``index`` holds the full reference state on every rank and has been given its shard with
+    ``index.set_shard(rank, world)``.  Returns the same (values, ids[, address]) on every rank."""
+    world = dist.get_world_size(group)
+    _, _, keys = index.search(x, k=k, return_keys=True)
+    if world == 1:
+        keys_all = keys[None]
+    else:
+        keys_all = torch.empty((world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
+        dist.all_gather_into_tensor(keys_all, keys, group=group)
+    values, ids, address = merge_gathered(keys_all, index._address2id)
+    return (values, ids, address) if return_address else (values, ids)
+
+
+def broadcast_state(index, src: int = 0, group=None):
+    """Replicate rank ``src``'s index buffers (after train/add) to every rank."""
+    rank = dist.get_rank(group)
+    dev = torch.device(index.device)
+    names = ["_storage", "_is_empty", "_cell_start", "_cell_size", "_cell_capacity", "_address2id"]
+    meta = [None]
+    if rank == src:
+        meta[0] = {n: (tuple(getattr(index, n).shape), getattr(index, n).dtype) for n in names}
+        meta[0]["vq"] = tuple(index.vq_codec.codebook.shape)
+        meta[0]["pq"] = tuple(index.pq_codec.codebook.shape)
+        meta[0]["max_id"] = index._max_id
+    dist.broadcast_object_list(meta, src=src, group=group)
+    m = meta[0]
+    for n in names:
+        if rank != src:
+            shape, dtype = m[n]
+            delattr(index, n)
+            index.register_buffer(n, torch.empty(shape, dtype=dtype, device=dev))
+        dist.broadcast(getattr(index, n), src=src, group=group)
+    vq = index.vq_codec.codebook if rank == src else torch.empty(m["vq"], dtype=torch.float32, device=dev)
+    pq = index.pq_codec.codebook if rank == src else torch.empty(m["pq"], dtype=torch.float32, device=dev)
+    dist.broadcast(vq, src=src, group=group)
+    dist.broadcast(pq, src=src, group=group)
+    if rank != src:
+        index.vq_codec.set_codebook(vq)
+        index.pq_codec.set_codebook(pq)
+        index._max_id = m["max_id"]
+    index._state_changed()

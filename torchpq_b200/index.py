@@ -224,6 +224,18 @@ class IVFPQIndex(StateModule):
                                          _lib.current_stream(dev)))
         return (values, ids, address) if return_address else (values, ids)
 
+    # ------------------------------------------------------------------ build side (torch ops, see build.py)
+    def train(self, x, force_retrain=False, seed=0):
+        if self.vq_codec.is_trained and self.pq_codec.is_trained and not force_retrain:
+            self.print_message("index is already trained", 1)                 # IVFPQIndex.py:235-238
+            return
+        from . import build
+        build.train(self, x, seed=seed)
+
+    def add(self, x, ids=None, return_address=False):
+        from . import build
+        return build.add(self, x, ids, return_address)
+
     def get_id_by_address(self, address):
         """BaseContainer.get_id_by_address (BaseContainer.py:58-65) -- plain tensor indexing, not on the hot path."""
         assert address.dtype == torch.int64
