@@ -151,7 +151,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
@@ -192,7 +192,7 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("TPQ_BENCH_WORKLOAD", "c3"), choices=list(WORKLOADS))
@@ -280,12 +280,12 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # samples across warm-up and both timed regions
     for i in range(args.warmup):
         step_device(i); step_e2e(i)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_dev = timed(step_device, args.steps)
-    clocks = sampler.stop() if sampler else None
     ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
     qps = nq * args.steps / (ms_dev / 1e3)
     qps_e2e = nq * args.steps / (ms_e2e / 1e3)
 
