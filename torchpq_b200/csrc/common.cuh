@@ -132,6 +132,57 @@ struct WarpTopK {
     return false;
   }
 };
+
+// CTA-wide top-k selector: ONE sorted list of kp keys shared by all warps of the CTA (so its
+// k-th entry is the true running k-th best of everything merged so far), one staging buffer
+// per warp.  A warp whose buffer is more than half full sorts it privately, then takes the
+// CTA lock and merges it into the shared list; the other warps keep scanning against the
+// (slightly stale, always valid) threshold in *thr.  Exact: a candidate is only ever dropped
+// when k better ones are already in the list.
+struct CtaTopK {
+  uint64_t* list;               // [kp] descending, shared by the CTA
+  unsigned long long* thr;      // k-th best of `list` (0 while fewer than k merged)
+  int* lock;
+  uint64_t* buf;                // [kTopkBuf] this warp's staging buffer
+  int kp, k, cnt;
+
+  // call from every thread of the CTA, then __syncthreads()
+  __device__ __forceinline__ void init(uint64_t* list_, unsigned long long* thr_, int* lock_, uint64_t* buf_,
+                                       int kp_, int k_) {
+    list = list_; thr = thr_; lock = lock_; buf = buf_; kp = kp_; k = k_; cnt = 0;
+    for (int i = threadIdx.x; i < kp; i += blockDim.x) list[i] = 0;
+    if (threadIdx.x == 0) { *thr = 0ull; *lock = 0; }
+  }
+  __device__ __forceinline__ uint64_t threshold() const { return *reinterpret_cast<volatile unsigned long long*>(thr); }
+
+  __device__ __forceinline__ void flush(int lane) {
+    if (cnt == 0) return;
+    for (int i = cnt + lane; i < kTopkBuf; i += 32) buf[i] = 0;
+    __syncwarp();
+    int nb = cnt <= 32 ? 32 : kTopkBuf;
+    warp_sort_desc(buf, nb, lane);
+    if (nb > kp) nb = kp;
+    if (lane == 0) { while (atomicCAS(lock, 0, 1) != 0) __nanosleep(20); }
+    __syncwarp();
+    __threadfence_block();
+    if (buf[0] > list[k - 1]) {                 // warp-uniform: anything left that still beats the k-th best?
+      warp_merge_desc(list, kp, buf, nb, lane);
+      if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(thr) = list[k - 1];
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicExch(lock, 0);
+    cnt = 0;
+  }
+  __device__ __forceinline__ void push(bool pass, uint64_t key, int lane) {
+    unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m == 0) return;
+    if (pass) buf[cnt + __popc(m & ((1u << lane) - 1))] = key;
+    cnt += __popc(m);
+    __syncwarp();
+    if (cnt > kTopkBuf - 32) flush(lane);
+  }
+};
 #endif  // __CUDACC__
 
 }  // namespace tpq

@@ -119,7 +119,7 @@ __device__ __forceinline__ float adc_block(const BlockRegs<MP>& r, const uint32_
   return (a0 + a1) + (a2 + a3);
 }
 
-struct ScanSmem { size_t lut, seg_blk0, seg_addr0, seg_prefix, thr, lists, total; };
+struct ScanSmem { size_t lut, seg_blk0, seg_addr0, seg_prefix, thr, lock, list, bufs, total; };
 static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp) {
   ScanSmem s; size_t off = 0;
   s.lut = off;        off += (size_t)((MP + 63) / 64) * 65536;
@@ -128,7 +128,9 @@ static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp) {
   s.seg_prefix = off; off += (size_t)(n_probe + 1) * 4;
   off = align_up(off, 8);
   s.thr = off;        off += 8;
-  s.lists = off;      off += (size_t)nw * (kp + kTopkBuf) * 8;
+  s.lock = off;       off += 8;
+  s.list = off;       off += (size_t)kp * 8;
+  s.bufs = off;       off += (size_t)nw * kTopkBuf * 8;
   s.total = off;
   return s;
 }
@@ -150,8 +152,6 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   int32_t*  seg_blk0   = reinterpret_cast<int32_t*>(smem + L.seg_blk0);
   uint32_t* seg_addr0  = reinterpret_cast<uint32_t*>(smem + L.seg_addr0);
   int32_t*  seg_prefix = reinterpret_cast<int32_t*>(smem + L.seg_prefix);
-  unsigned long long* cta_thr = reinterpret_cast<unsigned long long*>(smem + L.thr);
-  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + L.lists);
   constexpr int MG = (MP + 63) / 64;
 
   const int qi = blockIdx.x / A.S, slice = blockIdx.x % A.S;  // query within this chunk
@@ -191,9 +191,10 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
-  if (tid == 0) *cta_thr = 0ull;
-  WarpTopK tk;
-  tk.init(lists + (size_t)warp * (A.kp + kTopkBuf), lists + (size_t)warp * (A.kp + kTopkBuf) + A.kp, A.kp, A.k, lane);
+  CtaTopK tk;
+  tk.init(reinterpret_cast<uint64_t*>(smem + L.list), reinterpret_cast<unsigned long long*>(smem + L.thr),
+          reinterpret_cast<int*>(smem + L.lock), reinterpret_cast<uint64_t*>(smem + L.bufs) + (size_t)warp * kTopkBuf,
+          A.kp, A.k);
   // lane's slot offsets: byte r%4 of off[r/4] = ((lane + r) & 31) * 4
   uint32_t off[8];
   #pragma unroll
@@ -208,21 +209,23 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   const int total = seg_prefix[P];
   const int b_begin = (int)(((int64_t)total * slice) / A.S);
   const int b_end = (int)(((int64_t)total * (slice + 1)) / A.S);
-  int seg = 0;
+  // current segment kept in registers; shared memory is touched only when a warp crosses into the next cell
+  int seg = 0, seg_lo = 0, seg_hi = seg_prefix[1], seg_b0 = seg_blk0[0];
+  uint32_t seg_a0 = seg_addr0[0];
   auto locate = [&](int b, int64_t& B, uint32_t& addr0) {
-    while (b >= seg_prefix[seg + 1]) ++seg;
-    const int rel = b - seg_prefix[seg];
-    B = (int64_t)seg_blk0[seg] + rel;
-    addr0 = seg_addr0[seg] + (uint32_t)rel * 32u;
+    if (b >= seg_hi) {
+      do { ++seg; seg_lo = seg_hi; seg_hi = seg_prefix[seg + 1]; } while (b >= seg_hi);
+      seg_b0 = seg_blk0[seg]; seg_a0 = seg_addr0[seg];
+    }
+    const int rel = b - seg_lo;
+    B = (int64_t)seg_b0 + rel;
+    addr0 = seg_a0 + (uint32_t)rel * 32u;
   };
   auto consume = [&](const BlockRegs<MP>& r) {
     const float score = adc_block<MP>(r, off, lut);
     const uint64_t key = make_key(score, r.addr0 + lane);
-    const uint64_t thr = *reinterpret_cast<volatile unsigned long long*>(cta_thr);
     const bool live = (r.valid >> lane) & 1u;
-    if (tk.push(live && key > thr, key, lane)) {
-      if (lane == 0) atomicMax(cta_thr, (unsigned long long)tk.kth());
-    }
+    tk.push(live && key > tk.threshold(), key, lane);
   };
 
   int b = b_begin + warp;
@@ -246,15 +249,8 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   }
   tk.flush(lane);
   __syncthreads();
-  #pragma unroll 1
-  for (int stride = 1; stride < NW; stride <<= 1) {
-    if ((warp % (2 * stride)) == 0 && warp + stride < NW)
-      warp_merge_desc(lists + (size_t)warp * (A.kp + kTopkBuf), A.kp,
-                      lists + (size_t)(warp + stride) * (A.kp + kTopkBuf), A.kp, lane);
-    __syncthreads();
-  }
   uint64_t* out = A.keys_out + ((size_t)q * A.S + slice) * A.k;
-  for (int i = tid; i < A.k; i += NW * 32) out[i] = lists[i];
+  for (int i = tid; i < A.k; i += NW * 32) out[i] = tk.list[i];
 }
 
 // ----------------------------------------------------------------------------- merge + decode

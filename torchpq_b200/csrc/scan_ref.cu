@@ -6,10 +6,10 @@
 //   __global__ ivfpq_topk / ivfpq_top1      torchpq/kernels/cuda/ivfpq_topk.cu:822-971, ivfpq_top1.cu:384-455
 //
 // Not a port: one CTA per query, but each WARP owns 32 consecutive addresses at a
-// time (one coalesced 128-byte load per 4-sub-quantizer plane), keeps its own sorted
-// top-k list in shared memory, filters against a CTA-wide threshold (so the common
-// case is one compare + one ballot per 32 vectors, no barrier), and the warps' lists
-// are tree-merged once at the end.  Scores are accumulated exactly as the reference
+// time (one coalesced 128-byte load per 4-sub-quantizer plane) and filters against the
+// CTA-wide running k-th best (so the common case is one compare + one ballot per 32
+// vectors, no barrier); survivors go to a per-warp staging buffer that is merged into
+// the CTA's single sorted top-k list under a lock (CtaTopK, common.cuh).  Scores are accumulated exactly as the reference
 // does: fp32, sub-quantizer 0..M-1 ascending, starting from 0.f.
 #include "common.cuh"
 
@@ -17,7 +17,7 @@ namespace tpq {
 
 struct RefScanSmem {
   // byte offsets into dynamic shared memory
-  size_t lut, seg_start, seg_size, seg_prefix, thr, lists, total;
+  size_t lut, seg_start, seg_size, seg_prefix, thr, lock, list, bufs, total;
 };
 
 static RefScanSmem ref_scan_smem(int M, int n_probe, int nw, int kp) {
@@ -29,7 +29,9 @@ static RefScanSmem ref_scan_smem(int M, int n_probe, int nw, int kp) {
   s.seg_prefix = off; off += (size_t)(n_probe + 1) * sizeof(int32_t);
   off = align_up(off, 8);
   s.thr = off;        off += 8;
-  s.lists = off;      off += (size_t)nw * (kp + kTopkBuf) * sizeof(uint64_t);
+  s.lock = off;       off += 8;
+  s.list = off;       off += (size_t)kp * sizeof(uint64_t);
+  s.bufs = off;       off += (size_t)nw * kTopkBuf * sizeof(uint64_t);
   s.total = off;
   return s;
 }
@@ -49,8 +51,6 @@ ivfpq_topk_ref_kernel(const uint32_t* __restrict__ data,        // [M/4, n_data]
   int64_t*  seg_start  = reinterpret_cast<int64_t*>(smem + L.seg_start);
   int32_t*  seg_size   = reinterpret_cast<int32_t*>(smem + L.seg_size);
   int32_t*  seg_prefix = reinterpret_cast<int32_t*>(smem + L.seg_prefix);
-  unsigned long long* cta_thr = reinterpret_cast<unsigned long long*>(smem + L.thr);
-  uint64_t* lists      = reinterpret_cast<uint64_t*>(smem + L.lists);
 
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -90,9 +90,10 @@ ivfpq_topk_ref_kernel(const uint32_t* __restrict__ data,        // [M/4, n_data]
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
-  if (tid == 0) *cta_thr = 0ull;
-  WarpTopK tk;
-  tk.init(lists + (size_t)warp * (kp + kTopkBuf), lists + (size_t)warp * (kp + kTopkBuf) + kp, kp, k, lane);
+  CtaTopK tk;
+  tk.init(reinterpret_cast<uint64_t*>(smem + L.list), reinterpret_cast<unsigned long long*>(smem + L.thr),
+          reinterpret_cast<int*>(smem + L.lock), reinterpret_cast<uint64_t*>(smem + L.bufs) + (size_t)warp * kTopkBuf,
+          kp, k);
   __syncthreads();
 
   const int total_chunks = seg_prefix[P];
@@ -118,23 +119,13 @@ ivfpq_topk_ref_kernel(const uint32_t* __restrict__ data,        // [M/4, n_data]
       }
     }
     const uint64_t key = make_key(score, (uint32_t)a);
-    const uint64_t thr = *reinterpret_cast<volatile unsigned long long*>(cta_thr);
-    if (tk.push(live && key > thr, key, lane)) {
-      if (lane == 0) atomicMax(cta_thr, (unsigned long long)tk.kth());
-    }
+    tk.push(live && key > tk.threshold(), key, lane);
   }
   tk.flush(lane);
   __syncthreads();
-  // tree-merge the per-warp lists into warp 0's
-  for (int stride = 1; stride < nw; stride <<= 1) {
-    if ((warp % (2 * stride)) == 0 && warp + stride < nw)
-      warp_merge_desc(lists + (size_t)warp * (kp + kTopkBuf), kp,
-                      lists + (size_t)(warp + stride) * (kp + kTopkBuf), kp, lane);
-    __syncthreads();
-  }
   // write-out: descending, (-inf, -1) padded  (ivfpq_topk.cu:966-970; IVFPQTopkCuda.py:118-120,142)
   for (int i = tid; i < k; i += blockDim.x) {
-    uint64_t key = lists[i];
+    uint64_t key = tk.list[i];
     values[(size_t)q * k + i]  = key ? key_score(key) : -INFINITY;
     address[(size_t)q * k + i] = key ? (int64_t)key_addr(key) : -1;
   }
