@@ -1,0 +1,57 @@
+"""Launch the reference's own CUDA kernels (prebuilt into oracle/_ref/ by build_ref.py) on torch tensors.
+
+TEST INFRASTRUCTURE: used by tests/ to pin the CPU oracle (and the product) against the real
+reference kernel on the GPU box, and by bench.py to report the reference kernel's own time on
+B200 beside ours.  Host logic restates IVFPQTopkCuda.topk (torchpq/kernels/IVFPQTopkCuda.py:81-142):
+tot_size, -inf / 0 initialised outputs padded to 2*nextpow2(ceil(k/2)), slice [:, :k].
+"""
+import ctypes as C
+import math
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REF = os.path.join(_HERE, "_ref")
+_libs = {}
+
+
+def lib_path(m, tpb=256):
+    return os.path.join(_REF, f"libref_ivfpq_topk_m{m}_tpb{tpb}.so")
+
+
+def available(m, tpb=256) -> bool:
+    return os.path.exists(lib_path(m, tpb))
+
+
+def _load(m, tpb=256):
+    key = (m, tpb)
+    if key not in _libs:
+        lib = C.CDLL(lib_path(m, tpb))
+        lib.ref_ivfpq_topk_launch.restype = C.c_int
+        lib.ref_ivfpq_topk_launch.argtypes = [C.c_void_p] * 9 + [C.c_int] * 4 + [C.c_void_p]
+        _libs[key] = lib
+    return _libs[key]
+
+
+def ivfpq_topk(data, precomputed, cell_start, cell_size, is_empty, n_probe_list, k, tpb=256):
+    """Reference kernel `ivfpq_topk` (kernels/cuda/ivfpq_topk.cu:822-971), 1 < k <= tpb.
+    Returns (values [nq,k] f32, address [nq,k] i64) exactly as IVFPQTopkCuda.topk does."""
+    m = data.shape[0] * 4
+    lib = _load(m, tpb)
+    n_data = data.shape[1]
+    n_query, n_probe = cell_start.shape
+    assert precomputed.shape == (m, n_query, 256) and 1 < k <= tpb
+    n_pow2 = 2 * (1 if math.ceil(k / 2) == 0 else 2 ** math.ceil(math.log2(math.ceil(k / 2))))
+    dev = data.device
+    tot_size = cell_size.sum(dim=1)
+    values = torch.empty(n_query, n_pow2, device=dev, dtype=torch.float32).fill_(float("-inf"))
+    indices = torch.zeros(n_query, n_pow2, device=dev, dtype=torch.int64)
+    args = [t.contiguous() for t in (data, precomputed, is_empty, cell_start, cell_size, tot_size, n_probe_list)]
+    rc = lib.ref_ivfpq_topk_launch(*[C.c_void_p(t.data_ptr()) for t in args],
+                                   C.c_void_p(values.data_ptr()), C.c_void_p(indices.data_ptr()),
+                                   n_data, n_query, n_probe, n_pow2,
+                                   C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"reference kernel launch failed: cudaError {rc}")
+    return values[:, :k], indices[:, :k]

@@ -128,3 +128,74 @@ def test_lut_and_coarse(cuda_device):
         assert torch.allclose(gs.cpu(), sims, rtol=1e-4, atol=1e-3)
         assert (gc.cpu() == cells).float().mean() > 0.99
         assert (gn.cpu() == npl).float().mean() > 0.98
+
+
+def test_sharded_scan_equals_unsharded(cuda_device):
+    """Cell-sharded search (dist.py) without NCCL: run every shard on this GPU, stack the packed keys the
+    way the all-gather would, merge with tpq_merge_topk -> bit-identical to the unsharded search."""
+    import torchpq_b200 as T
+    torch.manual_seed(9)
+    st = B.build_state(torch.randn(64, 6000), 16, 32, vq_iters=2, pq_iters=1)
+    st.n_probe = 8
+    x = torch.randn(64, 300).cuda()
+    ix = make_index(st)
+    v0, i0, a0 = ix.search(x, k=40, return_address=True)
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            ix.set_shard(r, world)
+            parts.append(ix.search(x, k=40, return_keys=True)[2])
+        v, i, a = T.fn.merge_topk(torch.stack(parts).contiguous(), ix._address2id)
+        assert torch.equal(v, v0) and torch.equal(a, a0) and torch.equal(i, i0)
+    ix.set_shard(0, 1)
+
+
+def test_small_batch_slices(cuda_device):
+    """nq small -> each query is split over several CTAs (slices) and merged: same answer as the oracle."""
+    st, queries = B.integer_state(64, 16, 32, 20000, seed=21, lo=-6, hi=7)
+    st.n_probe, st.use_smart_probing = 16, False
+    ix = make_index(st)
+    for nq in (1, 3, 40):
+        x = queries(nq, qseed=nq)
+        ov, oi, oa = O.search(st, x, k=64, return_address=True)
+        v, i, a = ix.search(x.cuda(), k=64, return_address=True)
+        assert np.array_equal(v.cpu().numpy(), ov) and np.array_equal(a.cpu().numpy(), oa)
+
+
+def test_build_side_matches_oracle_placement(cuda_device):
+    """container_add on the GPU (torch ops, build.py) places items exactly where the oracle's restatement of
+    CellContainer.add does, including an expansion and a second add."""
+    from torchpq_b200 import build
+    import torchpq_b200 as T
+    rng = np.random.default_rng(4)
+    st = O.empty_state(32, 8, 16, 8)
+    ix = T.IVFPQIndex(32, 8, 16, initial_size=8, device="cuda:0")
+    for n in (700, 300):
+        codes = rng.integers(0, 256, (8, n)).astype(np.uint8)
+        cells = rng.integers(0, 16, n)
+        _, adr = O.container_add(st, codes, cells)
+        _, gadr = build.container_add(ix, torch.from_numpy(codes).cuda(), torch.from_numpy(cells).cuda(), return_address=True)
+        assert np.array_equal(gadr.cpu().numpy(), adr)
+    for name, ref in (("_storage", st.storage), ("_is_empty", st.is_empty), ("_cell_start", st.cell_start),
+                      ("_cell_size", st.cell_size), ("_cell_capacity", st.cell_capacity), ("_address2id", st.address2id)):
+        assert np.array_equal(getattr(ix, name).cpu().numpy(), ref), name
+
+
+def test_train_add_search_end_to_end(cuda_device):
+    """train -> add -> search through the public API only; recall equals the oracle's on the same state."""
+    import torchpq_b200 as T
+    torch.manual_seed(1)
+    base = torch.randn(32, 20000, device="cuda")
+    ix = T.IVFPQIndex(32, 16, 64, initial_size=64, device="cuda:0")
+    ix.train(base[:, :8000].contiguous())
+    ids = ix.add(base)
+    assert ids.shape[0] == 20000 and ix.n_items == 20000
+    ix.n_probe = 16
+    x = torch.randn(32, 200, device="cuda")
+    v, i = ix.search(x, k=10)
+    import bench
+    st = bench.to_oracle_state(ix)
+    ov, oi = O.search(st, x.cpu(), k=10)
+    assert_close_results(v.cpu().numpy(), i.cpu().numpy(), ov, oi, rtol=1e-3, min_overlap=0.995)
+    truth = O.exact_topk(base.cpu(), x.cpu(), 10, "euclidean").numpy()
+    assert abs(O.recall_at_k(i.cpu().numpy(), truth) - O.recall_at_k(oi, truth)) <= 1e-3

@@ -18,6 +18,8 @@
 //     a CTA-wide k-th-best, lists tree-merged at the end.
 // Sub-quantizer sums are fp32 in four interleaved partial sums (exact for integer LUTs;
 // ~1e-7 relative otherwise -- the reference's m-ascending order lives in scan_ref.cu).
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace tpq {
@@ -144,8 +146,8 @@ struct ScanArgs {
   int nq, q_base, n_probe, k, kp, S;
 };
 
-template <int MP, int NW>
-__global__ void __launch_bounds__(NW * 32, (MP <= 64 ? 2 : 1))
+template <int MP, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* lut = smem;                                       // L.lut == 0 by construction
@@ -340,17 +342,16 @@ static SearchWs search_ws(const tpq_index* ix, int nq, int n_probe, int k) {
   return w;
 }
 
-template <int MP>
+template <int MP, int NW, int MINB>
 static int launch_scan(const tpq_index* ix, const float* x, const int64_t* cells, const int64_t* npl,
                        int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st) {
-  constexpr int NW = 8;
   const int kp = next_pow2(k < 32 ? 32 : k);
   ScanSmem L = scan_smem(MP, n_probe, NW, kp);
   if (L.total > 227 * 1024) {
     set_error("scan: M=%d n_probe=%d k=%d needs %zu B of shared memory (> 227 KB)", ix->n_subvectors, n_probe, k, L.total);
     return TPQ_ERR_UNSUPPORTED;
   }
-  auto kern = ivfpq_scan_kernel<MP, NW>;
+  auto kern = ivfpq_scan_kernel<MP, NW, MINB>;
   TPQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   const int MG = (MP + 63) / 64;
   const int dsub = ix->d_vector / ix->n_subvectors;
@@ -392,13 +393,24 @@ static int check_index(const tpq_index* ix) {
 
 static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cells, const int64_t* npl,
                          int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st) {
+#define TPQ_SCAN_ARGS ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st
+  // tuning knob for experiments (scripts/sweep_scan.py): TPQ_SCAN_CFG = "<warps>x<min CTAs/SM>"
+  const char* cfg = getenv("TPQ_SCAN_CFG");
+  if (cfg && ix->m_pad == 64) {
+    if (!strcmp(cfg, "8x2"))  return launch_scan<64, 8, 2>(TPQ_SCAN_ARGS);
+    if (!strcmp(cfg, "8x3"))  return launch_scan<64, 8, 3>(TPQ_SCAN_ARGS);
+    if (!strcmp(cfg, "12x2")) return launch_scan<64, 12, 2>(TPQ_SCAN_ARGS);
+    if (!strcmp(cfg, "16x1")) return launch_scan<64, 16, 1>(TPQ_SCAN_ARGS);
+    if (!strcmp(cfg, "4x4"))  return launch_scan<64, 4, 4>(TPQ_SCAN_ARGS);
+    if (!strcmp(cfg, "4x6"))  return launch_scan<64, 4, 6>(TPQ_SCAN_ARGS);
+  }
   switch (ix->m_pad) {
-    case 32:  return launch_scan<32>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
-    case 64:  return launch_scan<64>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
-    case 96:  return launch_scan<96>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
-    case 128: return launch_scan<128>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
-    case 160: return launch_scan<160>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
-    case 192: return launch_scan<192>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+    case 32:  return launch_scan<32, 8, 2>(TPQ_SCAN_ARGS);
+    case 64:  return launch_scan<64, 8, 2>(TPQ_SCAN_ARGS);
+    case 96:  return launch_scan<96, 8, 1>(TPQ_SCAN_ARGS);
+    case 128: return launch_scan<128, 8, 1>(TPQ_SCAN_ARGS);
+    case 160: return launch_scan<160, 8, 1>(TPQ_SCAN_ARGS);
+    case 192: return launch_scan<192, 8, 1>(TPQ_SCAN_ARGS);
     default:
       set_error("n_subvectors=%d (padded %d) > 192 is not supported by the scan-layout path", ix->n_subvectors, ix->m_pad);
       return TPQ_ERR_UNSUPPORTED;

@@ -30,8 +30,9 @@ def sharded_search(index, x: torch.Tensor, k: int, group=None, return_address: b
     if world == 1:
         keys_all = keys[None]
     else:
-        keys_all = torch.empty((world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
+        keys_all = torch.empty((world * keys.shape[0], keys.shape[1]), dtype=keys.dtype, device=keys.device)
         dist.all_gather_into_tensor(keys_all, keys, group=group)
+        keys_all = keys_all.view(world, keys.shape[0], keys.shape[1])
     values, ids, address = merge_gathered(keys_all, index._address2id)
     return (values, ids, address) if return_address else (values, ids)
 
