@@ -139,14 +139,19 @@ static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp) {
 
 struct ScanArgs {
   const uint8_t* codes; const uint32_t* valid; const int32_t* cell_block_start; const int64_t* cell_start;
-  const float* lut_scan;          // [nq_chunk][MG][256][64]
+  const float* lut_scan;          // [nq_chunk][MG][256][64] (staged-LUT variant, DSUB == 0)
+  const float* x;                 // [d, nq] queries (in-CTA LUT variant)
+  const float* cbt;               // pq_codebook_t [256, MP, dsub]
+  int M, metric;
   const int64_t* cells;           // [nq, n_probe]
   const int64_t* n_probe_list;    // [nq]
   uint64_t* keys_out;             // [nq, S, k]
   int nq, q_base, n_probe, k, kp, S;
 };
 
-template <int MP, int NW, int MINB>
+// DSUB > 0: the CTA builds its query's LUT itself from the (L2-resident) transposed codebook -- no LUT
+// round trip through HBM, no LUT workspace.  DSUB == 0: the LUT was written by lut_scan_kernel and is copied in.
+template <int MP, int NW, int MINB, int DSUB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -160,12 +165,48 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   const int q = A.q_base + qi;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // --- stage LUT (MG * 64 KB, coalesced 16-byte copies)
-  {
+  if constexpr (DSUB == 0) {
+    // --- stage LUT (MG * 64 KB, coalesced 16-byte copies)
     const float4* src = reinterpret_cast<const float4*>(A.lut_scan + (size_t)qi * MG * 16384);
     float4* dst = reinterpret_cast<float4*>(lut);
     #pragma unroll 4
     for (int i = tid; i < MG * 4096; i += NW * 32) dst[i] = __ldg(src + i);
+  } else {
+    // --- build the LUT in place (PQCodec.py:62-75; MultiKMeans.py:183-223; same arithmetic as lut.cu).
+    // Lane l owns sub-quantizers m = 32 h + l: reads of the transposed codebook are contiguous across the
+    // warp and the store bank is l, so both sides are conflict-free / coalesced.
+    constexpr int NH = MP / 32;
+    float xr[NH][DSUB], a2[NH];
+    #pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      const int m = 32 * h + lane;
+      float s2 = 0.f;
+      #pragma unroll
+      for (int i = 0; i < DSUB; ++i) {
+        const float v = (m < A.M) ? __ldg(A.x + (size_t)(m * DSUB + i) * A.nq + q) : 0.f;
+        xr[h][i] = v;
+        s2 = __fadd_rn(s2, __fmul_rn(v, v));
+      }
+      a2[h] = s2;
+    }
+    float* lutf = reinterpret_cast<float*>(lut);
+    #pragma unroll 2
+    for (int c = warp; c < 256; c += NW) {
+      #pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float* p = A.cbt + ((size_t)c * MP + 32 * h + lane) * DSUB;
+        float pv[DSUB];
+        if constexpr (DSUB == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); pv[0] = t.x; pv[1] = t.y; }
+        else if constexpr (DSUB == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w; }
+        else { for (int i = 0; i < DSUB; ++i) pv[i] = __ldg(p + i); }
+        float dot = 0.f, b2 = 0.f;
+        #pragma unroll
+        for (int i = 0; i < DSUB; ++i) { dot = fmaf(xr[h][i], pv[i], dot); b2 = __fadd_rn(b2, __fmul_rn(pv[i], pv[i])); }
+        float y = dot;
+        if (A.metric == TPQ_METRIC_EUCLIDEAN) y = __fsub_rn(__fsub_rn(__fmul_rn(dot, 2.f), a2[h]), b2);
+        lutf[(h >> 1) * 16384 + c * 64 + (h & 1) * 32 + lane] = y;
+      }
+    }
   }
   // --- probe segments (same visiting rules as scan_ref.cu / ivfpq_topk.cu:837-870)
   int P = (int)A.n_probe_list[q];
@@ -223,11 +264,13 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
     B = (int64_t)seg_b0 + rel;
     addr0 = seg_a0 + (uint32_t)rel * 32u;
   };
-  auto consume = [&](const BlockRegs<MP>& r) {
+  uint64_t thr = 0;
+  auto consume = [&](const BlockRegs<MP>& r, bool refresh) {
     const float score = adc_block<MP>(r, off, lut);
     const uint64_t key = make_key(score, r.addr0 + lane);
     const bool live = (r.valid >> lane) & 1u;
-    tk.push(live && key > tk.threshold(), key, lane);
+    if (refresh) thr = tk.threshold();                    // running k-th best; read every other block
+    tk.push(live && key > thr, key, lane);
   };
 
   int b = b_begin + warp;
@@ -239,12 +282,12 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
     for (;;) {
       bool more = b + NW < b_end;
       if (more) { locate(b + NW, B, a0); load_block<MP>(rb, A.codes, A.valid, B, a0, lane); }
-      consume(ra);
+      consume(ra, true);
       if (!more) break;
       b += NW;
       more = b + NW < b_end;
       if (more) { locate(b + NW, B, a0); load_block<MP>(ra, A.codes, A.valid, B, a0, lane); }
-      consume(rb);
+      consume(rb, false);
       if (!more) break;
       b += NW;
     }
@@ -323,6 +366,15 @@ static int pick_slices(int nq, int k) {
   return s > 64 ? 64 : s;
 }
 
+// LUT source: built inside the scan CTA when d/M is small (the codebook slice a CTA must read, M*dsub KB,
+// is then no bigger than a couple of LUTs), staged through HBM otherwise.  TPQ_LUT_MODE=staged|fused overrides.
+static int fused_dsub(const tpq_index* ix) {
+  const int dsub = ix->d_vector / ix->n_subvectors;
+  const char* mode = getenv("TPQ_LUT_MODE");
+  if (mode && !strcmp(mode, "staged")) return 0;
+  return (dsub == 1 || dsub == 2 || dsub == 4) ? dsub : 0;
+}
+
 struct SearchWs {
   size_t coarse, probe_sims, cells, npl, xnorm, lut, keys, total;
 };
@@ -336,32 +388,35 @@ static SearchWs search_ws(const tpq_index* ix, int nq, int n_probe, int k) {
   w.cells = off;      off += align_up((size_t)nq * n_probe * 8, 256);
   w.npl = off;        off += align_up((size_t)nq * 8, 256);
   w.xnorm = off;      off += align_up((size_t)nq * ix->d_vector * 4, 256);
-  w.lut = off;        off += align_up((size_t)chunk * MG * 65536, 256);
+  w.lut = off;        off += fused_dsub(ix) ? 0 : align_up((size_t)chunk * MG * 65536, 256);
   w.keys = off;       off += align_up((size_t)nq * S * k * 8, 256);
   w.total = off;
   return w;
 }
 
-template <int MP, int NW, int MINB>
-static int launch_scan(const tpq_index* ix, const float* x, const int64_t* cells, const int64_t* npl,
-                       int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st) {
+template <int MP, int NW, int MINB, int DSUB>
+static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cells, const int64_t* npl,
+                         int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st) {
   const int kp = next_pow2(k < 32 ? 32 : k);
   ScanSmem L = scan_smem(MP, n_probe, NW, kp);
   if (L.total > 227 * 1024) {
     set_error("scan: M=%d n_probe=%d k=%d needs %zu B of shared memory (> 227 KB)", ix->n_subvectors, n_probe, k, L.total);
     return TPQ_ERR_UNSUPPORTED;
   }
-  auto kern = ivfpq_scan_kernel<MP, NW, MINB>;
+  auto kern = ivfpq_scan_kernel<MP, NW, MINB, DSUB>;
   TPQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   const int MG = (MP + 63) / 64;
   const int dsub = ix->d_vector / ix->n_subvectors;
   for (int q0 = 0; q0 < nq; q0 += kQueryChunk) {
     const int n = (nq - q0) < kQueryChunk ? (nq - q0) : kQueryChunk;
-    size_t xs_bytes = (size_t)(ix->d_vector + MP) * 4;
-    lut_scan_kernel<<<n, 256, xs_bytes, st>>>(x, ix->pq_codebook_t, ix->pq_norm_t, ix->d_vector, ix->n_subvectors, MP,
-                                              nq, q0, ix->metric, lut_ws);
-    TPQ_LAUNCH_CHECK("lut_scan_kernel");
+    if (DSUB == 0) {
+      size_t xs_bytes = (size_t)(ix->d_vector + MP) * 4;
+      lut_scan_kernel<<<n, 256, xs_bytes, st>>>(x, ix->pq_codebook_t, ix->pq_norm_t, ix->d_vector, ix->n_subvectors, MP,
+                                                nq, q0, ix->metric, lut_ws);
+      TPQ_LAUNCH_CHECK("lut_scan_kernel");
+    }
     ScanArgs A;
+    A.x = x; A.cbt = ix->pq_codebook_t; A.M = ix->n_subvectors; A.metric = ix->metric;
     A.codes = ix->codes_scan; A.valid = ix->block_valid; A.cell_block_start = ix->cell_block_start;
     A.cell_start = ix->cell_start; A.lut_scan = lut_ws; A.cells = cells; A.n_probe_list = npl; A.keys_out = keys;
     A.nq = nq; A.q_base = q0; A.n_probe = n_probe; A.k = k; A.kp = kp; A.S = S;
@@ -373,6 +428,17 @@ static int launch_scan(const tpq_index* ix, const float* x, const int64_t* cells
     (void)MG; (void)dsub;
   }
   return TPQ_OK;
+}
+
+template <int MP, int NW, int MINB>
+static int launch_scan(const tpq_index* ix, const float* x, const int64_t* cells, const int64_t* npl,
+                       int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st) {
+  switch (fused_dsub(ix)) {
+    case 1:  return launch_scan_d<MP, NW, MINB, 1>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+    case 2:  return launch_scan_d<MP, NW, MINB, 2>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+    case 4:  return launch_scan_d<MP, NW, MINB, 4>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+    default: return launch_scan_d<MP, NW, MINB, 0>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+  }
 }
 
 static int check_index(const tpq_index* ix) {
