@@ -134,6 +134,23 @@ int tpq_ivfpq_search_cells(const tpq_index* index, const float* x_dn, const int6
                            float* values, int64_t* ids, int64_t* address, uint64_t* keys_out,
                            void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ k-means / codec neighbours of the path
+ * tpq_max_sim: MultiKMeans assignment, MaxSimCuda(dim=2, mode "tn") (kernels/MaxSimCuda.py:184-238,
+ *   kernels/cuda/max_sim.cu:182-309; caller clustering/MultiKMeans.py:314-333):
+ *   data [l, d, n], centroids [l, d, k] -> maxsims [l, n] f32, labels [l, n] i64.
+ *   metric EUCLIDEAN: sum_e -(x-c)^2 (direct form, max_sim.cu:78-98); COSINE: sum_e x*c ("inner").
+ *   Ties: lowest centroid index (the reference's cross-tile label write is racy, max_sim.cu:173-178).
+ * tpq_compute_centroids: ComputeCentroidsCuda (kernels/ComputeCentroidsCuda.py:43-81, kernels/cuda/compute_centroids.cu:9-86):
+ *   data [l, d, n], labels [l, n] i64 -> centroids [l, d, k] = member mean, 0 for an empty cluster.
+ * tpq_pq_decode: PQDecodeCuda (kernels/PQDecodeCuda.py:38-65, kernels/cuda/pq_decode.cu:7-53):
+ *   codebook [M, dsub, 256], code [M, n] u8 -> out [M*dsub, n] f32. */
+int tpq_max_sim(const float* data, const float* centroids, int l, int d, int64_t n, int k, int metric,
+                float* maxsims, int64_t* labels, void* stream);
+size_t tpq_compute_centroids_workspace_bytes(int l, int k);
+int tpq_compute_centroids(const float* data, const int64_t* labels, int l, int d, int64_t n, int k,
+                          float* centroids, void* ws, size_t ws_bytes, void* stream);
+int tpq_pq_decode(const float* codebook, const uint8_t* code, int M, int dsub, int64_t n, float* out, void* stream);
+
 /* ------------------------------------------------------------------ measurement hook (bench.py roofline leg)
  * When enabled, every scan-kernel launch is bracketed by CUDA events on its own stream;
  * tpq_profile_scan_ms waits for them and returns the summed duration and launch count since

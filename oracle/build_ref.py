@@ -55,12 +55,93 @@ def build_ivfpq_topk(m, tpb=256, n_cs=4, stack_capacity=2):
     return out
 
 
+def _compile(name, code, extra=()):
+    os.makedirs(OUT, exist_ok=True)
+    out = os.path.join(OUT, f"lib{name}.so")
+    with tempfile.TemporaryDirectory() as td:
+        cu = os.path.join(td, f"{name}.cu")
+        open(cu, "w").write(code)
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", *extra,
+                               "-shared", "-Xcompiler", "-fPIC", "-w", "-o", out, cu])
+    return out
+
+
+MAX_SIM_LAUNCHER = r'''
+#include <cuda_runtime.h>
+extern "C" int ref_max_sim_tn_launch(const float* A, const float* B, float* C, long long* D,
+                                     int M, int N, int K, int DIM, int L, void* stream) {
+  dim3 grid = DIM == 1 ? dim3((N + 127) / 128, (M + 127) / 128, L) : dim3((M + 127) / 128, (N + 127) / 128, L);
+  max_sim_tn<<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, D, M, N, K, DIM);
+  return (int)cudaGetLastError();
+}
+'''
+
+
+def build_max_sim(distfn="thread_nseuclidean", tag="euclidean"):
+    """MaxSimCuda.__init__ (kernels/MaxSimCuda.py:17-68): m/n/k/dim left dynamic, options --maxrregcount=128
+    --use_fast_math; launch as _call_tn (:184-238)."""
+    src = open(os.path.join(REF, "max_sim.cu")).read()
+    code = (src.replace("_M_", "M").replace("_N_", "N").replace("_K_", "K").replace("_DIM_", "DIM")
+            .replace("_DISTFN_", distfn))
+    return _compile(f"ref_max_sim_{tag}", code + MAX_SIM_LAUNCHER, ("-maxrregcount=128", "-use_fast_math"))
+
+
+CENTROIDS_LAUNCHER = r'''
+#include <cuda_runtime.h>
+#undef int64_t
+extern "C" int ref_compute_centroids_launch(const float* data, const long long* labels, float* C,
+                                            int m, int n, int e, int k, void* stream) {
+  dim3 grid(m, (k + %(DK)d - 1) / %(DK)d, (e + %(DE)d - 1) / %(DE)d);
+  int smem = %(DK)d * (%(DE)d + 1) * 4;
+  cudaFuncSetAttribute(compute_centroids, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  compute_centroids<<<grid, 256, smem, (cudaStream_t)stream>>>(data, labels, C, m, n, e, k);
+  return (int)cudaGetLastError();
+}
+'''
+
+
+def build_compute_centroids(dk, de=1, tpb=256):
+    """ComputeCentroidsCuda.__init__/__call__ (kernels/ComputeCentroidsCuda.py:23-81); de=1, dk=min(k,4096)
+    as MultiKMeans constructs it (clustering/MultiKMeans.py:67-79)."""
+    import math
+    src = open(os.path.join(REF, "compute_centroids.cu")).read()
+    code = (src.replace("_DE_", str(de)).replace("_DK_", str(dk)).replace("_TPB_", str(tpb))
+            .replace("_NITERS_", str(math.ceil(dk / tpb))))
+    # NVRTC (what the reference uses) has no <stdint.h>, so the source typedefs int64_t itself; under nvcc
+    # that clashes with the system typedef.  A one-line preprocessor prelude renames the source's own
+    # typedef -- the reference text itself is untouched.
+    prelude = "#include <cuda_runtime.h>\n#define int64_t ref_int64_t\n"
+    return _compile(f"ref_compute_centroids_dk{dk}", prelude + code + CENTROIDS_LAUNCHER % {"DK": dk, "DE": de})
+
+
+DECODE_LAUNCHER = r'''
+#include <cuda_runtime.h>
+extern "C" int ref_pq_decode_launch(const float* codebook, const unsigned char* code, float* result,
+                                    int M, int D, int N, void* stream) {
+  dim3 grid((M + 1) / 2, (D + 7) / 8);
+  int smem = 8 * 2 * 256 * 4;
+  pq_decode<<<grid, 256, smem, (cudaStream_t)stream>>>(codebook, code, result, M, D, N);
+  return (int)cudaGetLastError();
+}
+'''
+
+
+def build_pq_decode(tm=2, td=8, tpb=256):
+    """PQDecodeCuda (kernels/PQDecodeCuda.py:8-65; tm=2, td=8 as codec/PQCodec.py:34 constructs it)."""
+    src = open(os.path.join(REF, "pq_decode.cu")).read()
+    code = src.replace("_TD_", str(td)).replace("_TM_", str(tm)).replace("_TPB_", str(tpb))
+    return _compile("ref_pq_decode", code + DECODE_LAUNCHER)
+
+
 def main():
     if not os.path.isdir(REF):
         print("oracle/_ref: /root/reference not present; keeping prebuilt files")
         return 0
-    for m in (8, 16, 32, 64, 120):
-        out = build_ivfpq_topk(m)
+    outs = [build_ivfpq_topk(m) for m in (8, 16, 32, 64, 120)]
+    outs += [build_max_sim("thread_nseuclidean", "euclidean"), build_max_sim("thread_matmul", "inner")]
+    outs += [build_compute_centroids(dk) for dk in (16, 256)]
+    outs += [build_pq_decode()]
+    for out in outs:
         print("built", os.path.relpath(out, HERE))
     return 0
 

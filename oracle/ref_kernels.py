@@ -55,3 +55,59 @@ def ivfpq_topk(data, precomputed, cell_start, cell_size, is_empty, n_probe_list,
     if rc != 0:
         raise RuntimeError(f"reference kernel launch failed: cudaError {rc}")
     return values[:, :k], indices[:, :k]
+
+
+# ---------------------------------------------------------------------------------- k-means / codec kernels
+def _so(name):
+    return os.path.join(_REF, f"lib{name}.so")
+
+
+def aux_available() -> bool:
+    return all(os.path.exists(_so(n)) for n in ("ref_max_sim_euclidean", "ref_max_sim_inner", "ref_pq_decode",
+                                                "ref_compute_centroids_dk256", "ref_compute_centroids_dk16"))
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def max_sim_tn(A, B, distance="euclidean", dim=2):
+    """MaxSimCuda._call_tn (kernels/MaxSimCuda.py:184-238): A [l, k, m], B [l, k, n] -> (vals, inds)."""
+    lib = C.CDLL(_so("ref_max_sim_" + ("euclidean" if distance == "euclidean" else "inner")))
+    lib.ref_max_sim_tn_launch.argtypes = [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]
+    l, k, m = A.shape
+    n = B.shape[2]
+    size = m if dim == 2 else n
+    vals = torch.full([l, size], float("-inf"), device=A.device, dtype=torch.float32)
+    inds = torch.empty([l, size], device=A.device, dtype=torch.long)
+    A, B = A.contiguous(), B.contiguous()
+    rc = lib.ref_max_sim_tn_launch(A.data_ptr(), B.data_ptr(), vals.data_ptr(), inds.data_ptr(), m, n, k, dim, l, _stream(A.device))
+    assert rc == 0, rc
+    return vals, inds
+
+
+def compute_centroids(data, labels, k):
+    """ComputeCentroidsCuda.__call__ (kernels/ComputeCentroidsCuda.py:43-81): data [m, d, n], labels [m, n]."""
+    dk = 256 if k >= 256 else 16
+    assert k in (16, 256)
+    lib = C.CDLL(_so(f"ref_compute_centroids_dk{dk}"))
+    lib.ref_compute_centroids_launch.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p]
+    m, d, n = data.shape
+    cent = torch.zeros(m, d, k, device=data.device, dtype=torch.float32)
+    data, labels = data.contiguous(), labels.contiguous()
+    rc = lib.ref_compute_centroids_launch(data.data_ptr(), labels.data_ptr(), cent.data_ptr(), m, n, d, k, _stream(data.device))
+    assert rc == 0, rc
+    return cent
+
+
+def pq_decode(codebook, code):
+    """PQDecodeCuda.__call__ (kernels/PQDecodeCuda.py:38-65)."""
+    lib = C.CDLL(_so("ref_pq_decode"))
+    lib.ref_pq_decode_launch.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p]
+    m, d, _ = codebook.shape
+    n = code.shape[1]
+    res = torch.ones(m, d, n, device=codebook.device, dtype=torch.float32)
+    codebook, code = codebook.contiguous(), code.contiguous()
+    rc = lib.ref_pq_decode_launch(codebook.data_ptr(), code.data_ptr(), res.data_ptr(), m, d, n, _stream(codebook.device))
+    assert rc == 0, rc
+    return res.reshape(m * d, n)

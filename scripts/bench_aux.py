@@ -1,0 +1,74 @@
+"""Secondary measurements on one B200 (run under gpurun; results -> gpurun_out/aux_bench.json):
+C5 MultiKMeans assignment (GB/s vs HBM roofline), compute_centroids, pq_decode, and search QPS on C2 / C4.
+CUDA events, 3 warm-ups, inputs larger than L2 where the workload allows."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torchpq_b200 as T
+import bench
+
+dev = torch.device("cuda:0")
+out = {}
+peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timeit(fn, reps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+which = sys.argv[1:] or ["c5", "centroids", "decode", "c2", "c4"]
+if "c5" in which or "centroids" in which:
+    l, d, n, k = 64, 64, 1_000_000, 256
+    data = torch.randn(l, d, n, device=dev)
+    cent = data[:, :, :k].contiguous()
+    if "c5" in which:
+        ms = timeit(lambda: T.fn.max_sim(data, cent), reps=3, warm=1)
+        byts = 4 * l * d * n + 4 * l * d * k + 12 * l * n
+        out["c5_max_sim"] = {"ms": ms, "algorithmic_GB": byts / 1e9, "GBps": byts / ms / 1e6, "frac_of_hbm_peak": byts / ms / 1e6 / peak,
+                             "tflops_gemm_form": 2.0 * l * n * d * k / ms / 1e9, "kernel": "max_sim_kernel (fp32 SIMT, exact)"}
+        print(out["c5_max_sim"], flush=True)
+    if "centroids" in which:
+        lab = T.fn.max_sim(data, cent)[1]
+        ms = timeit(lambda: T.fn.compute_centroids(data, lab, k), reps=3, warm=1)
+        byts = 4 * l * d * n + 8 * l * n + 4 * l * d * k
+        out["c5_compute_centroids"] = {"ms": ms, "algorithmic_GB": byts / 1e9, "GBps": byts / ms / 1e6, "frac_of_hbm_peak": byts / ms / 1e6 / peak}
+        print(out["c5_compute_centroids"], flush=True)
+    del data
+if "decode" in which:
+    M, dsub, n = 64, 2, 10_000_000
+    cb = torch.randn(M, dsub, 256, device=dev)
+    code = torch.randint(0, 256, (M, n), dtype=torch.uint8, device=dev)
+    ms = timeit(lambda: T.fn.pq_decode(cb, code))
+    byts = M * n + 4 * M * dsub * n
+    out["pq_decode_10M"] = {"ms": ms, "algorithmic_GB": byts / 1e9, "GBps": byts / ms / 1e6, "frac_of_hbm_peak": byts / ms / 1e6 / peak}
+    print(out["pq_decode_10M"], flush=True)
+    del code
+for name in ("c2", "c4"):
+    if name not in which:
+        continue
+    wl = bench.WORKLOADS[name]
+    index, base = bench.build_index(wl, dev)
+    nq = 10000 if name == "c2" else 1000
+    xs = [x.to(dev) for x in bench.gen_queries(wl[1], nq, 4, dev)]
+    k = wl[5]
+    T._lib.lib.tpq_profile_enable(0)
+    i = [0]
+    def step():
+        index.search(xs[i[0] % 4], k=k); i[0] += 1
+    ms = timeit(step, reps=10)
+    truth = bench.exact_truth(base, xs[0][:, :500].contiguous(), k, wl[6])
+    rec = bench.recall(index.search(xs[0][:, :500].contiguous(), k=k)[1], truth)
+    out[f"{name}_search"] = {"nq": nq, "ms_per_batch": ms, "qps": nq / ms * 1e3, "recall_at_100": rec, "workload": wl[8]}
+    print(out[f"{name}_search"], flush=True)
+    del index, base
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/aux_bench.json", "w"), indent=1)

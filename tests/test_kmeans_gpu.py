@@ -1,0 +1,67 @@
+"""GPU parity of tpq_max_sim / tpq_compute_centroids / tpq_pq_decode against the oracle and against the
+reference's own kernels (oracle/_ref)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kmeans_oracle as K, ref_kernels as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("l,d,n,k", [(3, 2, 1000, 256), (2, 16, 700, 40), (1, 64, 513, 256), (4, 8, 300, 300)])
+@pytest.mark.parametrize("distance", ["euclidean", "cosine"])
+def test_max_sim(cuda_device, l, d, n, k, distance):
+    import torchpq_b200 as T
+    torch.manual_seed(l * 7 + d)
+    data, cent = torch.randn(l, d, n), torch.randn(l, d, k)
+    osim, olab = K.max_sim(data.numpy(), cent.numpy(), distance)
+    sim, lab = T.fn.max_sim(data.cuda(), cent.cuda(), distance)
+    sim, lab = sim.cpu().numpy(), lab.cpu().numpy()
+    assert np.array_equal(sim, osim)                       # same fmaf chain -> bit-identical
+    assert np.array_equal(lab, olab)
+    if R.aux_available():                                  # the reference's own max_sim_tn kernel
+        rv, ri = R.max_sim_tn(data.cuda(), cent.cuda(), "euclidean" if distance == "euclidean" else "inner", dim=2)
+        assert np.array_equal(rv.cpu().numpy(), osim)
+        # the reference's label write races across its 128-wide centroid tiles (max_sim.cu:173-178):
+        # compare where the winner is unique
+        rl = ri.cpu().numpy()
+        assert (rl == olab).mean() > 0.999
+
+
+def test_max_sim_integer_ties_lowest_index(cuda_device):
+    import torchpq_b200 as T
+    rng = np.random.default_rng(0)
+    data = torch.from_numpy(rng.integers(-2, 3, (2, 4, 500)).astype(np.float32))
+    cent = torch.from_numpy(rng.integers(-2, 3, (2, 4, 300)).astype(np.float32))   # many duplicate centroids
+    osim, olab = K.max_sim(data.numpy(), cent.numpy())
+    sim, lab = T.fn.max_sim(data.cuda(), cent.cuda())
+    assert np.array_equal(lab.cpu().numpy(), olab) and np.array_equal(sim.cpu().numpy(), osim)
+
+
+@pytest.mark.parametrize("l,d,n,k", [(3, 2, 5000, 256), (2, 16, 3000, 16), (1, 130, 20000, 256), (2, 8, 100, 1000)])
+def test_compute_centroids(cuda_device, l, d, n, k):
+    import torchpq_b200 as T
+    torch.manual_seed(d)
+    data = torch.randn(l, d, n)
+    labels = torch.randint(0, max(1, k - 3), (l, n))       # the last clusters stay empty -> 0
+    oc = K.compute_centroids(data.numpy(), labels.numpy(), k)
+    c = T.fn.compute_centroids(data.cuda(), labels.cuda(), k).cpu().numpy()
+    assert np.allclose(c, oc, rtol=1e-5, atol=1e-6)
+    assert (c[:, :, k - 3:] == 0).all()
+    if R.aux_available() and k in (16, 256):
+        rc = R.compute_centroids(data.cuda(), labels.cuda(), k).cpu().numpy()
+        assert np.allclose(rc, oc, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("M,dsub,n", [(8, 4, 1000), (64, 2, 4096), (3, 8, 17), (120, 8, 333)])
+def test_pq_decode(cuda_device, M, dsub, n):
+    import torchpq_b200 as T
+    torch.manual_seed(M)
+    cb = torch.randn(M, dsub, 256)
+    code = torch.randint(0, 256, (M, n), dtype=torch.uint8)
+    o = K.pq_decode(cb.numpy(), code.numpy())
+    g = T.fn.pq_decode(cb.cuda(), code.cuda()).cpu().numpy()
+    assert np.array_equal(g, o)
+    if R.aux_available():
+        assert np.array_equal(R.pq_decode(cb.cuda(), code.cuda()).cpu().numpy(), o)

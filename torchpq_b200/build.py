@@ -1,9 +1,10 @@
 """Index build side (train / encode / add) -- the callers *before* the search hot path.
 
-SURVEY.md section 8(f) rank 1-2 ("next" rows).  This first version expresses the reference's
-semantics with plain PyTorch tensor ops on the index device so that large synthetic indexes
-can be built on the GPU for the search benchmark; it is NOT the measured path and uses no
-custom kernels yet.  Semantics followed:
+SURVEY.md section 8(f) rank 1-2 ("next" rows).  The two compute steps (assignment = tpq_max_sim,
+centroid update = tpq_compute_centroids) are the library's CUDA kernels; the container bookkeeping
+(index of appearance, expansion, write addresses) is expressed with PyTorch tensor ops on the index
+device.  It is what builds the large synthetic indexes for the search benchmark; it is NOT the
+measured path.  Semantics followed:
 
     IVFPQIndex.train        torchpq/index/IVFPQIndex.py:234-260  (VQ: <=15 Lloyd iters, PQ: <=25)
     KMeans / MultiKMeans    torchpq/clustering/KMeans.py:399-438, MultiKMeans.py:415-453
@@ -20,17 +21,10 @@ from __future__ import annotations
 import torch
 
 
-def _assign(data: torch.Tensor, cent: torch.Tensor, budget: int = 1 << 30) -> torch.Tensor:
-    """data [l, d, n], cent [l, d, k] -> labels [l, n] int64 (arg-max of -|x-c|^2; |x|^2 is constant per row)."""
-    l, d, n = data.shape
-    out = torch.empty(l, n, dtype=torch.long, device=data.device)
-    c2 = (cent ** 2).sum(dim=1)                                  # [l, k]
-    per = max(1, budget // max(1, l * cent.shape[2]))             # <= `budget` similarity entries at a time
-    for s in range(0, n, per):
-        a = data[:, :, s:s + per]
-        sim = torch.baddbmm(-c2[:, None, :], a.transpose(1, 2), cent, alpha=2.0)   # [l, m, k]
-        out[:, s:s + per] = sim.argmax(dim=2)
-    return out
+def _assign(data: torch.Tensor, cent: torch.Tensor) -> torch.Tensor:
+    """data [l, d, n], cent [l, d, k] -> labels [l, n] int64: tpq_max_sim (exact -sum (x-c)^2, lowest index on ties)."""
+    from . import fn
+    return fn.max_sim(data.contiguous(), cent.contiguous(), "euclidean")[1]
 
 
 def multi_kmeans(data: torch.Tensor, k: int, max_iter: int, tol: float = 1e-4, seed: int = 0) -> torch.Tensor:
@@ -41,12 +35,10 @@ def multi_kmeans(data: torch.Tensor, k: int, max_iter: int, tol: float = 1e-4, s
     cent = data[:, :, pick].clone()
     if cent.shape[2] < k:
         cent = torch.cat([cent, torch.zeros(l, d, k - cent.shape[2], device=data.device)], dim=2)
-    ones = torch.ones(l, n, device=data.device)
+    from . import fn
     for _ in range(max_iter):
         lab = _assign(data, cent)
-        sums = torch.zeros(l, d, k, device=data.device).scatter_add_(2, lab[:, None, :].expand(l, d, n), data)
-        cnt = torch.zeros(l, k, device=data.device).scatter_add_(1, lab, ones)
-        new = torch.where(cnt[:, None, :] > 0, sums / cnt.clamp(min=1)[:, None, :], torch.zeros((), device=data.device))
+        new = fn.compute_centroids(data, lab, k)
         shift = (new - cent).pow(2).sum(dim=1).sqrt().mean()
         cent = new
         if float(shift) < tol:

@@ -92,6 +92,46 @@ class IVFPQTopk:
         return values, address
 
 
+def max_sim(data, centroids, distance="euclidean"):
+    """MultiKMeans.get_labels / MaxSimCuda(dim=2): data [l, d, n], centroids [l, d, k] ->
+    (maxsims [l, n] f32, labels [l, n] i64)."""
+    a, b = _cuda_f32(data, "data"), _cuda_f32(centroids, "centroids")
+    assert a.dim() == 3 and b.dim() == 3 and a.shape[:2] == b.shape[:2]
+    l, d, n = a.shape
+    k = b.shape[2]
+    sims = torch.empty(l, n, dtype=torch.float32, device=a.device)
+    labels = torch.empty(l, n, dtype=torch.long, device=a.device)
+    check(lib.tpq_max_sim(ptr(a), ptr(b), l, d, n, k, _lib.METRIC[distance], ptr(sims), ptr(labels),
+                          _lib.current_stream(a.device)))
+    return sims, labels
+
+
+def compute_centroids(data, labels, k):
+    """ComputeCentroidsCuda.__call__: data [l, d, n], labels [l, n] i64 -> centroids [l, d, k]."""
+    a = _cuda_f32(data, "data")
+    assert labels.dtype == torch.int64 and labels.shape == (a.shape[0], a.shape[2])
+    labels = labels.contiguous()
+    l, d, n = a.shape
+    cent = torch.empty(l, d, k, dtype=torch.float32, device=a.device)
+    ws_bytes = lib.tpq_compute_centroids_workspace_bytes(l, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+    check(lib.tpq_compute_centroids(ptr(a), ptr(labels), l, d, n, k, ptr(cent), ptr(ws), ws_bytes,
+                                    _lib.current_stream(a.device)))
+    return cent
+
+
+def pq_decode(codebook, code):
+    """PQDecodeCuda.__call__: codebook [M, dsub, 256], code [M, n] u8 -> [M*dsub, n] f32."""
+    cb = _cuda_f32(codebook, "codebook")
+    assert code.dtype == torch.uint8 and code.dim() == 2 and code.shape[0] == cb.shape[0] and cb.shape[2] == 256
+    code = code.contiguous()
+    M, dsub, _ = cb.shape
+    n = code.shape[1]
+    out = torch.empty(M * dsub, n, dtype=torch.float32, device=cb.device)
+    check(lib.tpq_pq_decode(ptr(cb), ptr(code), M, dsub, n, ptr(out), _lib.current_stream(cb.device)))
+    return out
+
+
 def merge_topk(keys, address2id):
     """keys [n_parts, nq, k] int64-viewed packed candidates (each part sorted) -> (values, ids, address)."""
     assert keys.dim() == 3 and keys.dtype == torch.int64 and keys.is_contiguous()

@@ -236,6 +236,21 @@ class IVFPQIndex(StateModule):
         from . import build
         return build.add(self, x, ids, return_address)
 
+    def encode(self, x):
+        """IVFPQIndex.encode (IVFPQIndex.py:262-287): x [d_vector, n] -> PQ codes [n_subvectors, n] uint8."""
+        assert len(x.shape) == 2 and x.shape[0] == self.d_vector
+        from . import build, fn
+        if self.distance == "cosine":
+            x = fn.normalize(x.contiguous())
+        sub = x.reshape(self.n_subvectors, self.d_subvector, x.shape[1])
+        return build._assign(sub, self.pq_codec.codebook).to(torch.uint8)
+
+    def decode(self, code):
+        """IVFPQIndex.decode (IVFPQIndex.py:289-314) -> PQCodec.decode (PQCodec.py:113-130): [M, n] u8 -> [d, n] f32."""
+        assert len(code.shape) == 2 and code.shape[0] == self.n_subvectors
+        from . import fn
+        return fn.pq_decode(self.pq_codec.codebook, code)
+
     def get_id_by_address(self, address):
         """BaseContainer.get_id_by_address (BaseContainer.py:58-65) -- plain tensor indexing, not on the hot path."""
         assert address.dtype == torch.int64
