@@ -86,40 +86,105 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
   return v;
 }
 
+// A block (32 vectors x MP code bytes) is consumed in UNITS of up to 64 sub-quantizers (4 chunks = 16 words per
+// lane), so the register footprint and the software pipeline are the same for every M: while unit u is being
+// looked up, unit u+1 (the next 64 sub-quantizers of the block, or the first unit of the warp's next block) is in flight.
 template <int MP>
-struct BlockRegs {
-  uint32_t w[MP / 4];
-  uint32_t valid;
-  uint32_t addr0;
+struct Units {
+  static constexpr int NSB = (MP + 63) / 64;
+  __host__ __device__ static constexpr int words(int sb) { return (sb == NSB - 1 && (MP % 64) != 0) ? 8 : 16; }
 };
 
-template <int MP>
-__device__ __forceinline__ void load_block(BlockRegs<MP>& r, const uint8_t* __restrict__ codes,
-                                           const uint32_t* __restrict__ valid, int64_t B, uint32_t addr0, int lane) {
-  const uint4* p = reinterpret_cast<const uint4*>(codes + (size_t)B * (MP * 32)) + lane;
+template <int MP, int SB>
+__device__ __forceinline__ void load_unit(uint32_t (&w)[16], const uint8_t* __restrict__ codes, int64_t B, int lane) {
+  const uint4* p = reinterpret_cast<const uint4*>(codes + (size_t)B * (MP * 32)) + SB * 128 + lane;
   #pragma unroll
-  for (int j = 0; j < MP / 16; ++j) {
-    uint4 v = ldg_stream(p + j * 32);
-    r.w[4 * j + 0] = v.x; r.w[4 * j + 1] = v.y; r.w[4 * j + 2] = v.z; r.w[4 * j + 3] = v.w;
+  for (int j = 0; j < Units<MP>::words(SB) / 4; ++j) {
+    const uint4 v = ldg_stream(p + j * 32);
+    w[4 * j + 0] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
   }
-  r.valid = __ldg(valid + B);
-  r.addr0 = addr0;
 }
 
-template <int MP>
-__device__ __forceinline__ float adc_block(const BlockRegs<MP>& r, const uint32_t (&off)[8], const uint8_t* lut) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+template <int MP, int SB>
+__device__ __forceinline__ void adc_unit(const uint32_t (&w)[16], const uint32_t (&off)[8], const uint8_t* lut, float (&acc)[4]) {
   #pragma unroll
-  for (int i = 0; i < MP / 4; ++i) {
-    const int h = i >> 3;                               // half-group (32 sub-quantizers = 8 words)
-    const int imm = (h >> 1) * 65536 + (h & 1) * 128;
-    a0 += lut_at<0>(lut, r.w[i], off[i & 7], imm);
-    a1 += lut_at<1>(lut, r.w[i], off[i & 7], imm);
-    a2 += lut_at<2>(lut, r.w[i], off[i & 7], imm);
-    a3 += lut_at<3>(lut, r.w[i], off[i & 7], imm);
+  for (int i = 0; i < Units<MP>::words(SB); ++i) {
+    const int imm = SB * 65536 + (i >> 3) * 128;        // group SB, half-group i/8
+    acc[0] += lut_at<0>(lut, w[i], off[i & 7], imm);
+    acc[1] += lut_at<1>(lut, w[i], off[i & 7], imm);
+    acc[2] += lut_at<2>(lut, w[i], off[i & 7], imm);
+    acc[3] += lut_at<3>(lut, w[i], off[i & 7], imm);
   }
-  return (a0 + a1) + (a2 + a3);
 }
+
+// Per-warp scan state.  regs[2][16] is the ping-pong pair of unit buffers; every index into it is a
+// compile-time constant after unrolling (PAR / SB are template parameters), so it lives in registers.
+template <int MP, int NW>
+struct Scanner {
+  static constexpr int NSB = Units<MP>::NSB;
+  const uint8_t* codes; const uint32_t* valid; const uint8_t* lut;
+  const int32_t* seg_prefix; const int32_t* seg_blk0; const uint32_t* seg_addr0;
+  int lane;
+  uint32_t off[8];
+  uint32_t regs[2][16];
+  CtaTopK tk;
+  uint64_t thr;
+  int seg, seg_lo, seg_hi, seg_b0; uint32_t seg_a0;     // current probe segment, cached in registers
+  int64_t B_cur, B_nxt; uint32_t a0_cur, a0_nxt, valid_cur, valid_nxt;
+
+  __device__ __forceinline__ void locate(int b, int64_t& B, uint32_t& addr0) {
+    if (b >= seg_hi) {
+      do { ++seg; seg_lo = seg_hi; seg_hi = seg_prefix[seg + 1]; } while (b >= seg_hi);
+      seg_b0 = seg_blk0[seg]; seg_a0 = seg_addr0[seg];
+    }
+    const int rel = b - seg_lo;
+    B = (int64_t)seg_b0 + rel;
+    addr0 = seg_a0 + (uint32_t)rel * 32u;
+  }
+  template <int PAR, int SB>
+  __device__ __forceinline__ void step(float (&acc)[4], bool has_next) {
+    constexpr int BUF = (PAR + SB) & 1;
+    if constexpr (SB + 1 < NSB) {
+      load_unit<MP, SB + 1>(regs[BUF ^ 1], codes, B_cur, lane);
+    } else {
+      if (has_next) { load_unit<MP, 0>(regs[BUF ^ 1], codes, B_nxt, lane); valid_nxt = __ldg(valid + B_nxt); }
+    }
+    adc_unit<MP, SB>(regs[BUF], off, lut, acc);
+    if constexpr (SB + 1 < NSB) step<PAR, SB + 1>(acc, has_next);
+  }
+  // consume the block at the cursor (its unit 0 is already in regs[PAR]); prefetch the next block's unit 0
+  template <int PAR>
+  __device__ __forceinline__ void process_block(bool has_next) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    step<PAR, 0>(acc, has_next);
+    const float score = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    const uint64_t key = make_key(score, a0_cur + lane);
+    const bool live = (valid_cur >> lane) & 1u;
+    if (PAR == 0) thr = tk.threshold();                  // running k-th best of the CTA
+    tk.push(live && key > thr, key, lane);
+    B_cur = B_nxt; a0_cur = a0_nxt; valid_cur = valid_nxt;
+  }
+  __device__ __forceinline__ void run(int b, int b_end) {
+    if (b >= b_end) return;
+    locate(b, B_cur, a0_cur);
+    load_unit<MP, 0>(regs[0], codes, B_cur, lane);
+    valid_cur = __ldg(valid + B_cur);
+    for (;;) {
+      bool more = b + NW < b_end;
+      if (more) locate(b + NW, B_nxt, a0_nxt);
+      process_block<0>(more);
+      if (!more) break;
+      b += NW;
+      if constexpr (NSB % 2 == 1) {                       // odd unit count: the buffers swap roles every block
+        more = b + NW < b_end;
+        if (more) locate(b + NW, B_nxt, a0_nxt);
+        process_block<1>(more);
+        if (!more) break;
+        b += NW;
+      }
+    }
+  }
+};
 
 struct ScanSmem { size_t lut, seg_blk0, seg_addr0, seg_prefix, thr, lock, list, bufs, total; };
 static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp) {
@@ -190,7 +255,7 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       a2[h] = s2;
     }
     float* lutf = reinterpret_cast<float*>(lut);
-    #pragma unroll 2
+    #pragma unroll 8
     for (int c = warp; c < 256; c += NW) {
       #pragma unroll
       for (int h = 0; h < NH; ++h) {
@@ -234,64 +299,29 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
-  CtaTopK tk;
-  tk.init(reinterpret_cast<uint64_t*>(smem + L.list), reinterpret_cast<unsigned long long*>(smem + L.thr),
-          reinterpret_cast<int*>(smem + L.lock), reinterpret_cast<uint64_t*>(smem + L.bufs) + (size_t)warp * kTopkBuf,
-          A.kp, A.k);
+  Scanner<MP, NW> sc;
+  sc.codes = A.codes; sc.valid = A.valid; sc.lut = lut;
+  sc.seg_prefix = seg_prefix; sc.seg_blk0 = seg_blk0; sc.seg_addr0 = seg_addr0; sc.lane = lane;
+  sc.tk.init(reinterpret_cast<uint64_t*>(smem + L.list), reinterpret_cast<unsigned long long*>(smem + L.thr),
+             reinterpret_cast<int*>(smem + L.lock), reinterpret_cast<uint64_t*>(smem + L.bufs) + (size_t)warp * kTopkBuf,
+             A.kp, A.k);
   // lane's slot offsets: byte r%4 of off[r/4] = ((lane + r) & 31) * 4
-  uint32_t off[8];
   #pragma unroll
   for (int i = 0; i < 8; ++i) {
     uint32_t v = 0;
     #pragma unroll
     for (int b = 0; b < 4; ++b) v |= (uint32_t)(((lane + 4 * i + b) & 31) * 4) << (8 * b);
-    off[i] = v;
+    sc.off[i] = v;
   }
   __syncthreads();
 
   const int total = seg_prefix[P];
   const int b_begin = (int)(((int64_t)total * slice) / A.S);
   const int b_end = (int)(((int64_t)total * (slice + 1)) / A.S);
-  // current segment kept in registers; shared memory is touched only when a warp crosses into the next cell
-  int seg = 0, seg_lo = 0, seg_hi = seg_prefix[1], seg_b0 = seg_blk0[0];
-  uint32_t seg_a0 = seg_addr0[0];
-  auto locate = [&](int b, int64_t& B, uint32_t& addr0) {
-    if (b >= seg_hi) {
-      do { ++seg; seg_lo = seg_hi; seg_hi = seg_prefix[seg + 1]; } while (b >= seg_hi);
-      seg_b0 = seg_blk0[seg]; seg_a0 = seg_addr0[seg];
-    }
-    const int rel = b - seg_lo;
-    B = (int64_t)seg_b0 + rel;
-    addr0 = seg_a0 + (uint32_t)rel * 32u;
-  };
-  uint64_t thr = 0;
-  auto consume = [&](const BlockRegs<MP>& r, bool refresh) {
-    const float score = adc_block<MP>(r, off, lut);
-    const uint64_t key = make_key(score, r.addr0 + lane);
-    const bool live = (r.valid >> lane) & 1u;
-    if (refresh) thr = tk.threshold();                    // running k-th best; read every other block
-    tk.push(live && key > thr, key, lane);
-  };
-
-  int b = b_begin + warp;
-  if (b < b_end) {
-    BlockRegs<MP> ra, rb;
-    int64_t B; uint32_t a0;
-    locate(b, B, a0);
-    load_block<MP>(ra, A.codes, A.valid, B, a0, lane);
-    for (;;) {
-      bool more = b + NW < b_end;
-      if (more) { locate(b + NW, B, a0); load_block<MP>(rb, A.codes, A.valid, B, a0, lane); }
-      consume(ra, true);
-      if (!more) break;
-      b += NW;
-      more = b + NW < b_end;
-      if (more) { locate(b + NW, B, a0); load_block<MP>(ra, A.codes, A.valid, B, a0, lane); }
-      consume(rb, false);
-      if (!more) break;
-      b += NW;
-    }
-  }
+  sc.thr = 0;
+  sc.seg = 0; sc.seg_lo = 0; sc.seg_hi = seg_prefix[1]; sc.seg_b0 = seg_blk0[0]; sc.seg_a0 = seg_addr0[0];
+  sc.run(b_begin + warp, b_end);
+  CtaTopK& tk = sc.tk;
   tk.flush(lane);
   __syncthreads();
   uint64_t* out = A.keys_out + ((size_t)q * A.S + slice) * A.k;
@@ -473,10 +503,10 @@ static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cel
   switch (ix->m_pad) {
     case 32:  return launch_scan<32, 8, 2>(TPQ_SCAN_ARGS);
     case 64:  return launch_scan<64, 8, 2>(TPQ_SCAN_ARGS);
-    case 96:  return launch_scan<96, 8, 1>(TPQ_SCAN_ARGS);
-    case 128: return launch_scan<128, 8, 1>(TPQ_SCAN_ARGS);
-    case 160: return launch_scan<160, 8, 1>(TPQ_SCAN_ARGS);
-    case 192: return launch_scan<192, 8, 1>(TPQ_SCAN_ARGS);
+    case 96:  return launch_scan<96, 16, 1>(TPQ_SCAN_ARGS);      // LUT >= 128 KB: one CTA per SM, so twice the warps
+    case 128: return launch_scan<128, 16, 1>(TPQ_SCAN_ARGS);
+    case 160: return launch_scan<160, 16, 1>(TPQ_SCAN_ARGS);
+    case 192: return launch_scan<192, 16, 1>(TPQ_SCAN_ARGS);
     default:
       set_error("n_subvectors=%d (padded %d) > 192 is not supported by the scan-layout path", ix->n_subvectors, ix->m_pad);
       return TPQ_ERR_UNSUPPORTED;
