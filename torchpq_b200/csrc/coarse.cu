@@ -11,29 +11,44 @@
 
 namespace tpq {
 
-// out[j] = sum_i x[i, j]^2  (separately rounded squares, ascending i -- torch's (a ** 2).sum(dim=-2))
-__global__ void col_sqnorm_kernel(const float* __restrict__ x, int d, int n, float* __restrict__ out) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+// Column reductions over a [d, n] matrix.  A CTA owns 32 columns; its 32 x 8 threads split the rows eight ways
+// (coalesced 128-byte row segments), partial sums meet in shared memory.  Row-group partials are combined in
+// ascending group order, so the result is deterministic.
+constexpr int CR_G = 8;     // row groups per CTA
+__device__ __forceinline__ float col_sumsq(const float* __restrict__ x, int d, int n, int j, int g, float (*part)[33], bool fma) {
   float s = 0.f;
-  for (int i = 0; i < d; ++i) {
-    float v = x[(size_t)i * n + j];
-    s = __fadd_rn(s, __fmul_rn(v, v));
+  if (j < n) {
+    for (int i = g; i < d; i += CR_G) {
+      const float v = x[(size_t)i * n + j];
+      s = fma ? fmaf(v, v, s) : __fadd_rn(s, __fmul_rn(v, v));
+    }
   }
-  out[j] = s;
+  part[g][threadIdx.x & 31] = s;
+  __syncthreads();
+  float t = 0.f;
+  #pragma unroll
+  for (int r = 0; r < CR_G; ++r) t = __fadd_rn(t, part[r][threadIdx.x & 31]);
+  return t;
+}
+
+// out[j] = sum_i x[i, j]^2   (torch's (a ** 2).sum(dim=-2): separately rounded squares)
+__global__ void __launch_bounds__(32 * CR_G)
+col_sqnorm_kernel(const float* __restrict__ x, int d, int n, float* __restrict__ out) {
+  __shared__ float part[CR_G][33];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+  const float t = col_sumsq(x, d, n, j, g, part, false);
+  if (g == 0 && j < n) out[j] = t;
 }
 
 // out[:, j] = x[:, j] / (||x[:, j]||_2 + 1e-9)   (util.py:38-43)
-__global__ void normalize_columns_kernel(const float* __restrict__ x, int d, int n, float* __restrict__ out) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * CR_G)
+normalize_columns_kernel(const float* __restrict__ x, int d, int n, float* __restrict__ out) {
+  __shared__ float part[CR_G][33];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+  const float t = col_sumsq(x, d, n, j, g, part, true);
   if (j >= n) return;
-  float s = 0.f;
-  for (int i = 0; i < d; ++i) {
-    float v = x[(size_t)i * n + j];
-    s = fmaf(v, v, s);
-  }
-  float nrm = __fadd_rn(sqrtf(s), 1e-9f);
-  for (int i = 0; i < d; ++i) out[(size_t)i * n + j] = __fdiv_rn(x[(size_t)i * n + j], nrm);
+  const float nrm = __fadd_rn(sqrtf(t), 1e-9f);
+  for (int i = g; i < d; i += CR_G) out[(size_t)i * n + j] = __fdiv_rn(x[(size_t)i * n + j], nrm);
 }
 
 // sims[q, c] = ((2 * sum_i x[i,q] * cb[i,c]) - xn[q]) - cn[c]        (metric.py:75-94)
@@ -181,7 +196,7 @@ using namespace tpq;
 extern "C" int tpq_normalize_columns(const float* x_dn, int d, int nq, float* out_dn, void* stream) {
   TPQ_REQUIRE(x_dn && out_dn && d > 0 && nq >= 0, "tpq_normalize_columns: bad argument");
   if (nq == 0) return TPQ_OK;
-  normalize_columns_kernel<<<(nq + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x_dn, d, nq, out_dn);
+  normalize_columns_kernel<<<(nq + 31) / 32, 32 * CR_G, 0, (cudaStream_t)stream>>>(x_dn, d, nq, out_dn);
   TPQ_LAUNCH_CHECK("normalize_columns_kernel");
   return TPQ_OK;
 }
@@ -209,8 +224,8 @@ extern "C" int tpq_coarse_probe(const float* x_dn, const float* vq_codebook, int
   float* sims = reinterpret_cast<float*>(w);  w += align_up((size_t)nq * n_cells * 4, 256);
   float* xn = reinterpret_cast<float*>(w);    w += align_up((size_t)nq * 4, 256);
   float* cn = reinterpret_cast<float*>(w);
-  col_sqnorm_kernel<<<(nq + 255) / 256, 256, 0, st>>>(x_dn, d, nq, xn);
-  col_sqnorm_kernel<<<(n_cells + 255) / 256, 256, 0, st>>>(vq_codebook, d, n_cells, cn);
+  col_sqnorm_kernel<<<(nq + 31) / 32, 32 * CR_G, 0, st>>>(x_dn, d, nq, xn);
+  col_sqnorm_kernel<<<(n_cells + 31) / 32, 32 * CR_G, 0, st>>>(vq_codebook, d, n_cells, cn);
   dim3 grid((n_cells + GB - 1) / GB, (nq + GB - 1) / GB);
   coarse_gemm_kernel<<<grid, 256, 0, st>>>(x_dn, vq_codebook, xn, cn, d, nq, n_cells, sims);
   TPQ_LAUNCH_CHECK("coarse_gemm_kernel");

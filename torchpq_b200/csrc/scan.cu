@@ -25,45 +25,62 @@
 namespace tpq {
 
 // ----------------------------------------------------------------------------- LUT in scan layout (global)
-// lut_scan[q][g][code][s] = LUT[64 g + s][q][code], zero for padding sub-quantizers.
-// Same arithmetic as lut.cu (PQCodec.py:62-75, MultiKMeans.py:183-223).
+// lut_scan[q][g][code][s] = LUT[64 g + s][q][code], zero for padding sub-quantizers.  Same arithmetic as lut.cu
+// (PQCodec.py:62-75, MultiKMeans.py:183-223).  Used when d/M is too large for the in-CTA build.
+// CTA = 256 codes x 16 sub-quantizers x LS_QT queries: every codebook value is loaded once (coalesced over the
+// code) and reused for LS_QT queries; query sub-vectors are broadcast from shared memory.
+constexpr int LS_QT = 8, LS_MT = 16;
 __global__ void __launch_bounds__(256)
-lut_scan_kernel(const float* __restrict__ x, const float* __restrict__ cbt, const float* __restrict__ nrm,
-                int d, int M, int MP, int nq, int q_base, int metric, float* __restrict__ lut_scan) {
-  extern __shared__ __align__(16) float xs[];            // [d] query, then [MP] |x_m|^2
-  const int q = q_base + blockIdx.x;
+lut_scan_kernel(const float* __restrict__ x, const float* __restrict__ cb, int d, int M, int MP, int nq,
+                int q_base, int n_chunk, int metric, float* __restrict__ lut_scan) {
+  extern __shared__ __align__(16) float xs[];            // [LS_QT][LS_MT * dsub] sub-vectors, then [LS_QT][LS_MT] |x_m|^2
   const int dsub = d / M;
-  float* a2s = xs + d;
-  for (int i = threadIdx.x; i < d; i += blockDim.x) xs[i] = x[(size_t)i * nq + q];
+  const int m0 = blockIdx.y * LS_MT;
+  const int q0 = blockIdx.x * LS_QT;                     // within this chunk
+  const int c = threadIdx.x;
+  float* a2s = xs + LS_QT * LS_MT * dsub;
+  for (int i = threadIdx.x; i < LS_QT * LS_MT * dsub; i += blockDim.x) {
+    const int qq = i / (LS_MT * dsub), r = i % (LS_MT * dsub);
+    const int row = m0 * dsub + r;
+    xs[i] = (q0 + qq < n_chunk && row < d) ? x[(size_t)row * nq + q_base + q0 + qq] : 0.f;
+  }
   __syncthreads();
-  for (int m = threadIdx.x; m < MP; m += blockDim.x) {
+  for (int i = threadIdx.x; i < LS_QT * LS_MT; i += blockDim.x) {
+    const float* v = xs + (size_t)i * dsub;
     float a2 = 0.f;
-    if (m < M) for (int i = 0; i < dsub; ++i) { float v = xs[m * dsub + i]; a2 = __fadd_rn(a2, __fmul_rn(v, v)); }
-    a2s[m] = a2;
+    for (int e = 0; e < dsub; ++e) a2 = __fadd_rn(a2, __fmul_rn(v[e], v[e]));
+    a2s[i] = a2;
   }
   __syncthreads();
   const int MG = (MP + 63) / 64;
-  float* out = lut_scan + (size_t)blockIdx.x * MG * 16384;
-  const int m4n = MP / 4;
-  for (int item = threadIdx.x; item < 256 * m4n; item += blockDim.x) {
-    const int c = item / m4n, m0 = (item % m4n) * 4;
-    float o[4];
+  for (int mm = 0; mm < LS_MT; ++mm) {
+    const int m = m0 + mm;
+    if (m >= MP) break;
+    float dot[LS_QT];
     #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int m = m0 + u;
+    for (int qq = 0; qq < LS_QT; ++qq) dot[qq] = 0.f;
+    float b2 = 0.f;
+    if (m < M) {
+      const float* p = cb + (size_t)m * dsub * 256 + c;
+      #pragma unroll 4
+      for (int e = 0; e < dsub; ++e) {
+        const float pv = __ldg(p + (size_t)e * 256);
+        b2 = __fadd_rn(b2, __fmul_rn(pv, pv));
+        #pragma unroll
+        for (int qq = 0; qq < LS_QT; ++qq) dot[qq] = fmaf(xs[(qq * LS_MT + mm) * dsub + e], pv, dot[qq]);
+      }
+    }
+    const int g = m >> 6, sl = m & 63;
+    #pragma unroll
+    for (int qq = 0; qq < LS_QT; ++qq) {
+      if (q0 + qq >= n_chunk) break;
       float y = 0.f;
       if (m < M) {
-        const float* p = cbt + ((size_t)c * MP + m) * dsub;
-        float dot = 0.f;
-        for (int i = 0; i < dsub; ++i) dot = fmaf(xs[m * dsub + i], p[i], dot);
-        y = dot;
-        if (metric == TPQ_METRIC_EUCLIDEAN)
-          y = __fsub_rn(__fsub_rn(__fmul_rn(dot, 2.f), a2s[m]), nrm[(size_t)c * MP + m]);
+        y = dot[qq];
+        if (metric == TPQ_METRIC_EUCLIDEAN) y = __fsub_rn(__fsub_rn(__fmul_rn(dot[qq], 2.f), a2s[qq * LS_MT + mm]), b2);
       }
-      o[u] = y;
+      lut_scan[((size_t)(q0 + qq) * MG + g) * 16384 + c * 64 + sl] = y;
     }
-    const int g = m0 >> 6, s = m0 & 63;
-    *reinterpret_cast<float4*>(out + (size_t)g * 16384 + c * 64 + s) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -440,9 +457,10 @@ static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cel
   for (int q0 = 0; q0 < nq; q0 += kQueryChunk) {
     const int n = (nq - q0) < kQueryChunk ? (nq - q0) : kQueryChunk;
     if (DSUB == 0) {
-      size_t xs_bytes = (size_t)(ix->d_vector + MP) * 4;
-      lut_scan_kernel<<<n, 256, xs_bytes, st>>>(x, ix->pq_codebook_t, ix->pq_norm_t, ix->d_vector, ix->n_subvectors, MP,
-                                                nq, q0, ix->metric, lut_ws);
+      size_t xs_bytes = (size_t)LS_QT * LS_MT * (dsub + 1) * 4;
+      dim3 lgrid((n + LS_QT - 1) / LS_QT, (MP + LS_MT - 1) / LS_MT);
+      lut_scan_kernel<<<lgrid, 256, xs_bytes, st>>>(x, ix->pq_codebook, ix->d_vector, ix->n_subvectors, MP,
+                                                    nq, q0, n, ix->metric, lut_ws);
       TPQ_LAUNCH_CHECK("lut_scan_kernel");
     }
     ScanArgs A;
@@ -478,7 +496,7 @@ static int check_index(const tpq_index* ix) {
   TPQ_REQUIRE(ix->n_subvectors % 4 == 0, "n_subvectors=%d must be a multiple of 4", ix->n_subvectors);
   TPQ_REQUIRE(ix->metric == TPQ_METRIC_EUCLIDEAN || ix->metric == TPQ_METRIC_COSINE,
               "unsupported distance (reference supports euclidean and cosine only)");
-  TPQ_REQUIRE(ix->vq_codebook && ix->cell_start && ix->address2id, "index is missing reference buffers");
+  TPQ_REQUIRE(ix->vq_codebook && ix->pq_codebook && ix->cell_start && ix->address2id, "index is missing reference buffers");
   TPQ_REQUIRE(ix->codes_scan || ix->n_blocks == 0, "index has no scan layout (call tpq_relayout_codes first)");
   TPQ_REQUIRE(ix->block_valid || ix->n_blocks == 0, "index has no scan layout (block_valid)");
   TPQ_REQUIRE(ix->cell_block_start && ix->pq_codebook_t && ix->pq_norm_t, "index has no scan layout (plan / codebook)");
