@@ -65,3 +65,39 @@ def test_pq_decode(cuda_device, M, dsub, n):
     assert np.array_equal(g, o)
     if R.aux_available():
         assert np.array_equal(R.pq_decode(cb.cuda(), code.cuda()).cpu().numpy(), o)
+
+
+def _exact_sim_of(data, cent, labels):
+    """fp32 fmaf-chain similarity of every point to the centroid `labels` picks (oracle arithmetic)."""
+    l, d, n = data.shape
+    out = np.zeros((l, n), np.float32)
+    for li in range(l):
+        c = cent[li][:, labels[li]]                           # [d, n]
+        acc = np.zeros(n, np.float32)
+        for e in range(d):
+            dif = (data[li, e] - c[e]).astype(np.float32)
+            acc = K._fma32(-dif, dif, acc)
+        out[li] = acc
+    return out
+
+
+@pytest.mark.parametrize("l,d,n,k", [(3, 64, 4096, 256), (2, 16, 1000, 40), (1, 8, 132, 256), (5, 32, 300, 100), (64, 64, 2048, 256)])
+def test_max_sim_tensor_core(cuda_device, l, d, n, k):
+    """TF32 tcgen05 assignment: labels equal the exact ones except between near-equidistant centroids, and the
+    reported similarity is the EXACT fp32 value of the chosen centroid."""
+    import torchpq_b200 as T
+    torch.manual_seed(l + d + k)
+    data, cent = torch.randn(l, d, n), torch.randn(l, d, k)
+    osim, olab = K.max_sim(data.numpy(), cent.numpy())
+    sim, lab = T.fn.max_sim(data.cuda(), cent.cuda(), exact=False)
+    torch.cuda.synchronize()
+    sim, lab = sim.cpu().numpy(), lab.cpu().numpy()
+    assert lab.min() >= 0 and lab.max() < k
+    agree = (lab == olab).mean()
+    assert agree >= 0.985, f"label agreement {agree}"
+    assert np.array_equal(sim, _exact_sim_of(data.numpy(), cent.numpy(), lab))
+    # where the label differs the chosen centroid is (almost) as close as the best one
+    bad = lab != olab
+    if bad.any():
+        rel = (osim[bad] - sim[bad]) / np.abs(osim[bad])
+        assert rel.min() >= 0 and rel.max() < 5e-3

@@ -57,7 +57,7 @@ SIGNATURES = {
     "tpq_search_workspace_bytes": (_SZ, [_IX, _I, _I, _I]),
     "tpq_ivfpq_search": (_I, [_IX, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _SZ, _P]),
     "tpq_ivfpq_search_cells": (_I, [_IX, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
-    "tpq_max_sim": (_I, [_P, _P, _I, _I, _I64, _I, _I, _P, _P, _P]),
+    "tpq_max_sim": (_I, [_P, _P, _I, _I, _I64, _I, _I, _I, _P, _P, _P]),
     "tpq_compute_centroids_workspace_bytes": (_SZ, [_I, _I]),
     "tpq_compute_centroids": (_I, [_P, _P, _I, _I, _I64, _I, _P, _P, _SZ, _P]),
     "tpq_pq_decode": (_I, [_P, _P, _I, _I, _I64, _P, _P]),

@@ -1,0 +1,321 @@
+// MultiKMeans assignment on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Replaces the reference's fused SIMT distance-GEMM + arg-max (torchpq/kernels/cuda/max_sim.cu:182-309,
+// 128x128 tiles, 8x8 register micro-tiles, float atomicMax epilogue) for the shape the PQ codec uses
+// (MultiKMeans.get_labels, clustering/MultiKMeans.py:314-333): data [l, d, n], centroids [l, d, k<=256].
+//
+//   label_i = argmax_j ( 2 <x_i, c_j> - |c_j|^2 )         (|x_i|^2 does not change the arg-max)
+//
+// The inner products run as TF32 UMMA (M=128 points x N<=256 centroids x K=8 per instruction), accumulators in
+// TMEM.  Operands are read by TMA exactly as they lie in HBM: both matrices are "MN-major" (points / centroids
+// contiguous), which tcgen05 accepts for TF32, so a TMA box of 32 columns x d rows with the 128-byte swizzle IS
+// the canonical UMMA shared-memory layout -- no transposition, no conversion pass.
+// The value written to `maxsims` is then recomputed EXACTLY (fp32, fmaf(-dif, dif, acc), e ascending, as
+// max_sim.cu:78-98) for the chosen centroid from the same shared-memory tiles, so values are bit-identical to the
+// exact kernel wherever the label agrees; labels can differ only where two centroids are within TF32 rounding
+// (~1e-3 relative) of each other.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 =
+// epilogue (one TMEM lane = one point per thread).  Three pipelines: A stages (TMA -> MMA + epilogue), the
+// resident B tile (reloaded when the CTA's tile range crosses into the next k-means), two TMEM accumulators.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace tpq {
+
+constexpr int TC_M = 128;          // points per tile
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 192;
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// UMMA shared-memory descriptor, MN-major operand, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (stride between 32-element MN groups) | SBO>>4 [32,46) (stride between
+// 8-row K groups) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+
+// element (row e, column c) of a [rows x 32-column] TMA box written with the 128-byte swizzle
+__device__ __forceinline__ uint32_t box_off(int e, int c) {
+  return (uint32_t)(e * 128 + ((((c >> 2) ^ (e & 7)) << 4) | ((c & 3) << 2)));
+}
+
+struct TcParams {
+  int l, d, n, k, kpad;          // kpad = k rounded up to 32 (TMA box granularity), N of the MMA = kpad
+  int tiles_per_l;               // ceil(n / 128)
+  float* maxsims; int64_t* labels;
+  const float* cent;             // for |c|^2 of padded columns nothing is read: TMA zero-fills
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c, TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int d = P.d;
+  const uint32_t box_bytes = (uint32_t)d * 128;                       // one 32-column box
+  const uint32_t b_bytes = (uint32_t)(P.kpad / 32) * box_bytes;
+  const uint32_t a_bytes = 4 * box_bytes;
+  uint8_t* sB = smem;                                                  // 1024-aligned (box_bytes is a multiple of 1024: d % 8 == 0)
+  uint8_t* sA = smem + b_bytes;
+  float* c2 = reinterpret_cast<float*>(sA + TC_STAGES * a_bytes);      // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(c2 + 256);
+  uint64_t* full_a = bars;                    // [STAGES]
+  uint64_t* empty_a = bars + TC_STAGES;       // [STAGES]
+  uint64_t* tmem_full = bars + 2 * TC_STAGES; // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint64_t* b_full = tmem_empty + 2;          // [1]
+  uint64_t* b_free = b_full + 1;              // [1]
+  uint64_t* c2_ready = b_free + 1;            // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(c2_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total_tiles = (long long)P.l * P.tiles_per_l;
+  const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
+  const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_c) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1 + 4); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&tmem_full[t], 1); mbar_init(&tmem_empty[t], 4); }
+    mbar_init(b_full, 1); mbar_init(b_free, 1 + 4); mbar_init(c2_ready, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_ptr)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int cur_l = -1; uint32_t bgen = 0;
+      long long it = 0;
+      for (long long t = t_begin; t < t_end; ++t, ++it) {
+        const int li = (int)(t / P.tiles_per_l), ti = (int)(t % P.tiles_per_l);
+        if (li != cur_l) {
+          if (cur_l >= 0) { mbar_wait(b_free, bgen & 1); ++bgen; }     // every MMA + epilogue read of the old B is done
+          mbar_expect_tx(b_full, b_bytes);
+          for (int g = 0; g < P.kpad / 32; ++g) tma_load_3d(sB + g * box_bytes, &map_c, b_full, g * 32, 0, li);
+          cur_l = li;
+        }
+        const int s = (int)(it % TC_STAGES); const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1;
+        mbar_wait(&empty_a[s], ph ^ 1);
+        mbar_expect_tx(&full_a[s], a_bytes);
+        for (int g = 0; g < 4; ++g) tma_load_3d(sA + s * a_bytes + g * box_bytes, &map_x, &full_a[s], ti * TC_M + g * 32, 0, li);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2,
+    // B=tf32 [10,13)=2, A MN-major bit15, B MN-major bit16, N>>3 [17,23), M>>4 [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(P.kpad >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    int cur_l = -1; uint32_t bgen = 0;
+    long long it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const int li = (int)(t / P.tiles_per_l);
+      if (li != cur_l) { mbar_wait(b_full, bgen & 1); ++bgen; cur_l = li; }
+      const int s = (int)(it % TC_STAGES); const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1;
+      const int tb = (int)(it & 1); const uint32_t tph = (uint32_t)(it >> 1) & 1;
+      mbar_wait(&tmem_empty[tb], tph ^ 1);
+      mbar_wait(&full_a[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t a0 = smem_u32(sA + s * a_bytes), b0 = smem_u32(sB);
+        for (int kb = 0; kb < d / 8; ++kb) {
+          const uint64_t da = umma_desc(a0 + kb * 1024, box_bytes, 1024);
+          const uint64_t db = umma_desc(b0 + kb * 1024, box_bytes, 1024);
+          umma_tf32(tmem_base + tb * 256, da, db, idesc, kb > 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_a[s]);                                      // MMA done with this A stage
+        umma_commit(&tmem_full[tb]);                                   // accumulator ready
+        const bool last_of_l = (t + 1 == t_end) || ((int)((t + 1) / P.tiles_per_l) != li);
+        if (last_of_l) umma_commit(b_free);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================================================== epilogue: thread = one point (TMEM lane)
+    const int quad = warp & 3;                                         // TMEM lanes [32 quad, 32 quad + 32)
+    const int row = quad * 32 + lane;                                  // point within the tile
+    const int et = threadIdx.x - 64;                                   // 0..127 among epilogue threads
+    int cur_l = -1; uint32_t bgen = 0;
+    long long it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const int li = (int)(t / P.tiles_per_l), ti = (int)(t % P.tiles_per_l);
+      const int s = (int)(it % TC_STAGES);
+      const int tb = (int)(it & 1); const uint32_t tph = (uint32_t)(it >> 1) & 1;
+      if (li != cur_l) {
+        // |c_j|^2 of the new centroid set, from the B tile in shared memory (2 columns per thread)
+        mbar_wait(b_full, bgen & 1); ++bgen; cur_l = li;
+        asm volatile("bar.sync 1, 128;" ::: "memory");                // nobody still reads the old c2
+        for (int j = et; j < 256; j += 128) {
+          float s2 = 0.f;
+          if (j < P.kpad) {
+            const uint8_t* bj = sB + (j >> 5) * box_bytes;
+            for (int e = 0; e < d; ++e) { const float v = *reinterpret_cast<const float*>(bj + box_off(e, j & 31)); s2 = fmaf(v, v, s2); }
+          }
+          c2[j] = (j < P.k) ? s2 : INFINITY;                           // padded columns can never win
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(&tmem_full[tb], tph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float best = -INFINITY; int besti = 0;
+      for (int c0 = 0; c0 < P.kpad; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * 256 + c0), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        #pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float sc = fmaf(2.f, __uint_as_float(v[j]), -c2[c0 + j]);
+          if (sc > best) { best = sc; besti = c0 + j; }                // strict '>' keeps the lowest index on ties
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (lane == 0) mbar_arrive(&tmem_empty[tb]);
+      // exact fp32 similarity of the chosen centroid (max_sim.cu:78-98 arithmetic)
+      const uint8_t* xa = sA + s * (size_t)a_bytes + (row >> 5) * box_bytes;
+      const uint8_t* cb = sB + (besti >> 5) * box_bytes;
+      float acc = 0.f;
+      for (int e = 0; e < d; ++e) {
+        const float xv = *reinterpret_cast<const float*>(xa + box_off(e, row & 31));
+        const float cv = *reinterpret_cast<const float*>(cb + box_off(e, besti & 31));
+        const float dif = xv - cv;
+        acc = fmaf(-dif, dif, acc);
+      }
+      const long long p = (long long)ti * TC_M + row;
+      if (p < P.n) {
+        P.maxsims[(size_t)li * P.n + p] = acc;
+        P.labels[(size_t)li * P.n + p] = besti;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&empty_a[s]);                                      // this warp is done reading the A stage
+        const bool last_of_l = (t + 1 == t_end) || ((int)((t + 1) / P.tiles_per_l) != li);
+        if (last_of_l) mbar_arrive(b_free);                            // ... and, for this k-means, the B tile
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [l][rows][cols] fp32, cols contiguous; box = 32 cols x rows x 1, 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const float* base, int l, int rows, long long cols) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return TPQ_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)l};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)cols * rows * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return TPQ_ERR_CUDA; }
+  return TPQ_OK;
+}
+
+// shapes the tensor-core kernel takes; everything else goes to the exact SIMT kernel
+bool assign_tc_supported(int l, int d, long long n, int k, const void* data, const void* cent) {
+  return l >= 1 && d >= 8 && d <= 64 && d % 8 == 0 && k >= 8 && k <= 256 && k % 4 == 0 && n % 4 == 0 && n >= 128 &&
+         n < (1ll << 31) && (reinterpret_cast<uintptr_t>(data) & 15) == 0 && (reinterpret_cast<uintptr_t>(cent) & 15) == 0;
+}
+
+int launch_assign_tc(const float* data, const float* cent, int l, int d, long long n, int k,
+                     float* maxsims, int64_t* labels, cudaStream_t st) {
+  CUtensorMap mx, mc;
+  if (int rc = make_map(&mx, data, l, d, n)) return rc;
+  if (int rc = make_map(&mc, cent, l, d, k)) return rc;
+  TcParams P;
+  P.l = l; P.d = d; P.n = (int)n; P.k = k; P.kpad = (k + 31) / 32 * 32;
+  P.tiles_per_l = (int)((n + TC_M - 1) / TC_M);
+  P.maxsims = maxsims; P.labels = labels; P.cent = cent;
+  const size_t box = (size_t)d * 128;
+  const size_t smem = (size_t)(P.kpad / 32) * box + (size_t)TC_STAGES * 4 * box + 256 * 4 + 32 * 8 + 1024;
+  TPQ_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long total = (long long)l * P.tiles_per_l;
+  int grid = (int)(total < sms ? total : sms);
+  assign_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mx, mc, P);
+  TPQ_LAUNCH_CHECK("assign_tc_kernel");
+  return TPQ_OK;
+}
+
+}  // namespace tpq
