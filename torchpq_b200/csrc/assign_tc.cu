@@ -8,15 +8,16 @@
 //
 // The inner products run as TF32 UMMA (M=128 points x N<=256 centroids x K=8 per instruction), accumulators in
 // TMEM.  Operands are read by TMA exactly as they lie in HBM: both matrices are "MN-major" (points / centroids
-// contiguous), which tcgen05 accepts for TF32, so a TMA box of 32 columns x d rows with the 128-byte swizzle IS
-// the canonical UMMA shared-memory layout -- no transposition, no conversion pass.
+// contiguous), which tcgen05 accepts for TF32, so a TMA box of 32 columns x d rows with the 128B/32B-atom swizzle
+// IS the canonical UMMA shared-memory layout -- no transposition, no conversion pass.
 // The value written to `maxsims` is then recomputed EXACTLY (fp32, fmaf(-dif, dif, acc), e ascending, as
 // max_sim.cu:78-98) for the chosen centroid from the same shared-memory tiles, so values are bit-identical to the
 // exact kernel wherever the label agrees; labels can differ only where two centroids are within TF32 rounding
 // (~1e-3 relative) of each other.
 //
-// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 =
-// epilogue (one TMEM lane = one point per thread).  Three pipelines: A stages (TMA -> MMA + epilogue), the
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 = arg-max
+// over the TMEM accumulator (4 lane quadrants x 2 column halves), warps 10..17 = finishers (exact similarity + stores),
+// two groups alternating tiles so the dependent fp32 chain of one tile overlaps the next tile's arg-max.  Three pipelines: A stages (TMA -> MMA + epilogue), the
 // resident B tile (reloaded when the CTA's tile range crosses into the next k-means), two TMEM accumulators.
 #include <cuda.h>
 #include "common.cuh"
@@ -25,7 +26,7 @@ namespace tpq {
 
 constexpr int TC_M = 128;          // points per tile
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 64 + 512;
 
 // ----------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -58,12 +59,14 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-// UMMA shared-memory descriptor, MN-major operand, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-// start>>4 [0,14) | LBO>>4 [16,30) (stride between 32-element MN groups) | SBO>>4 [32,46) (stride between
-// 8-row K groups) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+// UMMA shared-memory descriptor, MN-major 32-bit operand.  For MN-major TF32 the only legal shared-memory layout is
+// SWIZZLE_128B_BASE32B (cutlass sm100_common.inl:92): 128-byte rows, the four 32-byte chunks of a row XOR-ed with
+// (row % 4) -- Swizzle<2,5,2> -- which is what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+// Fields (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) (stride between 32-element
+// MN groups) | SBO>>4 [32,46) (stride between 4-row K groups) | version=1 [46,48) | layout_type=1 [61,64)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         (1ull << 46) | (2ull << 61);
+         (1ull << 46) | (1ull << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -86,9 +89,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
 }
 
-// element (row e, column c) of a [rows x 32-column] TMA box written with the 128-byte swizzle
+// element (row e, column c) of a [rows x 32-column] TMA box written with the 128B / 32B-atom swizzle
 __device__ __forceinline__ uint32_t box_off(int e, int c) {
-  return (uint32_t)(e * 128 + ((((c >> 2) ^ (e & 7)) << 4) | ((c & 3) << 2)));
+  return (uint32_t)(e * 128 + ((((c >> 3) ^ (e & 3)) << 5) | ((c & 7) << 2)));
 }
 
 struct TcParams {
@@ -96,7 +99,9 @@ struct TcParams {
   int tiles_per_l;               // ceil(n / 128)
   float* maxsims; int64_t* labels;
   const float* cent;             // for |c|^2 of padded columns nothing is read: TMA zero-fills
+  float* dbg;                    // debug: raw accumulators of tile 0 of CTA 0, [128][256]
 };
+static float* g_tc_dbg = nullptr;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c, TcParams P) {
@@ -107,7 +112,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const uint32_t a_bytes = 4 * box_bytes;
   uint8_t* sB = smem;                                                  // 1024-aligned (box_bytes is a multiple of 1024: d % 8 == 0)
   uint8_t* sA = smem + b_bytes;
-  float* c2 = reinterpret_cast<float*>(sA + TC_STAGES * a_bytes);      // [256]
+  uint8_t* sAx = sA + TC_STAGES * a_bytes;                             // 4 boxes x 1 KB: the constant "ones" K-block of A
+  uint8_t* sBx = sAx + 4 * 1024;                                       // 8 boxes x 1 KB: -|c_j|^2/2 as (hi, lo) rows of B
+  float* c2 = reinterpret_cast<float*>(sBx + 8 * 1024);                // [256] scratch
   uint64_t* bars = reinterpret_cast<uint64_t*>(c2 + 256);
   uint64_t* full_a = bars;                    // [STAGES]
   uint64_t* empty_a = bars + TC_STAGES;       // [STAGES]
@@ -116,7 +123,11 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   uint64_t* b_full = tmem_empty + 2;          // [1]
   uint64_t* b_free = b_full + 1;              // [1]
   uint64_t* c2_ready = b_free + 1;            // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(c2_ready + 1);
+  uint64_t* cand_full = c2_ready + 1;         // [2]
+  uint64_t* cand_empty = cand_full + 2;       // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(cand_empty + 2);
+  float* cand_v = reinterpret_cast<float*>(tmem_ptr + 2);              // [2 tile parities][2 column halves][128] partial winners
+  int* cand_i = reinterpret_cast<int*>(cand_v + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total_tiles = (long long)P.l * P.tiles_per_l;
@@ -127,10 +138,19 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_c) : "memory");
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1 + 4); }
-    for (int t = 0; t < 2; ++t) { mbar_init(&tmem_full[t], 1); mbar_init(&tmem_empty[t], 4); }
-    mbar_init(b_full, 1); mbar_init(b_free, 1 + 4); mbar_init(c2_ready, 4);
+    for (int t = 0; t < 2; ++t) { mbar_init(&tmem_full[t], 1); mbar_init(&tmem_empty[t], 8); mbar_init(&cand_full[t], 8); mbar_init(&cand_empty[t], 4); }
+    mbar_init(b_full, 1); mbar_init(b_free, 1 + 8); mbar_init(c2_ready, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // extra K-block operands: A rows 0,1 = 1.0 (rows 2..7 = 0); B rows filled per k-means by the epilogue
+  for (int i = threadIdx.x; i < 3 * 1024; i += blockDim.x) reinterpret_cast<uint32_t*>(sAx)[i] = 0u;   // sAx + sBx = 12 KB
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int c = threadIdx.x;
+    *reinterpret_cast<float*>(sAx + (c >> 5) * 1024 + box_off(0, c & 31)) = 1.f;
+    *reinterpret_cast<float*>(sAx + (c >> 5) * 1024 + box_off(1, c & 31)) = 1.f;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_ptr)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -169,7 +189,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     long long it = 0;
     for (long long t = t_begin; t < t_end; ++t, ++it) {
       const int li = (int)(t / P.tiles_per_l);
-      if (li != cur_l) { mbar_wait(b_full, bgen & 1); ++bgen; cur_l = li; }
+      if (li != cur_l) { mbar_wait(b_full, bgen & 1); mbar_wait(c2_ready, bgen & 1); ++bgen; cur_l = li; }
       const int s = (int)(it % TC_STAGES); const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1;
       const int tb = (int)(it & 1); const uint32_t tph = (uint32_t)(it >> 1) & 1;
       mbar_wait(&tmem_empty[tb], tph ^ 1);
@@ -178,10 +198,12 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       if (elect_one()) {
         const uint32_t a0 = smem_u32(sA + s * a_bytes), b0 = smem_u32(sB);
         for (int kb = 0; kb < d / 8; ++kb) {
-          const uint64_t da = umma_desc(a0 + kb * 1024, box_bytes, 1024);
-          const uint64_t db = umma_desc(b0 + kb * 1024, box_bytes, 1024);
+          const uint64_t da = umma_desc(a0 + kb * 1024, box_bytes, 512);
+          const uint64_t db = umma_desc(b0 + kb * 1024, box_bytes, 512);
           umma_tf32(tmem_base + tb * 256, da, db, idesc, kb > 0 ? 1u : 0u);
         }
+        // + 1 * hi(-|c|^2/2) + 1 * lo(-|c|^2/2): the accumulator then holds <x,c> - |c|^2/2, whose arg-max is the label
+        umma_tf32(tmem_base + tb * 256, umma_desc(smem_u32(sAx), 1024, 512), umma_desc(smem_u32(sBx), 1024, 512), idesc, 1u);
         umma_commit(&empty_a[s]);                                      // MMA done with this A stage
         umma_commit(&tmem_full[tb]);                                   // accumulator ready
         const bool last_of_l = (t + 1 == t_end) || ((int)((t + 1) / P.tiles_per_l) != li);
@@ -189,66 +211,119 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
       __syncwarp();
     }
+  } else if (warp < 10) {
+    // ===================================================== arg-max warps: 8 warps = 4 TMEM lane quadrants x 2 column halves.
+    // A warp may only touch TMEM lanes [32 (warp % 4), +32).  Thread (quad, lane) owns point `row` and scans the 128
+    // accumulator columns of its half; the two partial winners of a row go to shared memory for the finisher warps.
+    const int quad = warp & 3;
+    const int ch = (warp - 2) >> 2;                                    // column half: columns [128 ch, 128 ch + 128)
+    const int row = quad * 32 + lane;
+    const int at = threadIdx.x - 64;                                   // 0..255 among arg-max threads = centroid column
+    int cur_l = -1; uint32_t bgen = 0;
+    long long it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const int li = (int)(t / P.tiles_per_l);
+      const int tb = (int)(it & 1); const uint32_t tph = (uint32_t)(it >> 1) & 1;
+      if (li != cur_l) {
+        // -|c_j|^2 / 2 of the new centroid set as (hi, lo) TF32 rows of the extra K-block of B
+        mbar_wait(b_full, bgen & 1); ++bgen; cur_l = li;
+        const int j = at;
+        float v = -1e30f;                                              // padded columns can never win
+        if (j < P.k) {
+          const uint8_t* bj = sB + (j >> 5) * box_bytes;
+          float s2 = 0.f;
+          for (int e = 0; e < d; ++e) { const float cv = *reinterpret_cast<const float*>(bj + box_off(e, j & 31)); s2 = fmaf(cv, cv, s2); }
+          v = -0.5f * s2;
+        }
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);   // exactly representable in TF32
+        const float lo = v - hi;
+        if (j < P.kpad) {
+          *reinterpret_cast<float*>(sBx + (j >> 5) * 1024 + box_off(0, j & 31)) = hi;
+          *reinterpret_cast<float*>(sBx + (j >> 5) * 1024 + box_off(1, j & 31)) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(c2_ready);
+      }
+      mbar_wait(&tmem_full[tb], tph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float best = -INFINITY; int besti = 0x7fffffff;
+      #pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int c0 = ch * 128 + half * 64;
+        if (c0 < P.kpad) {
+          uint32_t v0[32], v1[32];
+          const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * 256 + c0);
+          tmem_ld32(ta, v0);
+          tmem_ld32(ta + 32, v1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (P.dbg && t == 0) {
+            for (int j = 0; j < 32; ++j) { P.dbg[row * 256 + c0 + j] = __uint_as_float(v0[j]); P.dbg[row * 256 + c0 + 32 + j] = __uint_as_float(v1[j]); }
+          }
+          const bool v1ok = c0 + 32 < P.kpad;                          // beyond kpad: stale TMEM
+          float b0 = -INFINITY, b1 = -INFINITY; int i0 = 0, i1 = 0;   // two independent chains for ILP
+          #pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float s0 = __uint_as_float(v0[j]);
+            const float s1 = v1ok ? __uint_as_float(v1[j]) : -INFINITY;
+            if (s0 > b0) { b0 = s0; i0 = j; }                          // strict '>' keeps the lowest index on ties
+            if (s1 > b1) { b1 = s1; i1 = 32 + j; }
+          }
+          if (b1 > b0) { b0 = b1; i0 = i1; }
+          if (b0 > best) { best = b0; besti = c0 + i0; }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[tb]);
+      mbar_wait(&cand_empty[tb], tph ^ 1);                             // finishers are done with this candidate buffer
+      cand_v[(tb * 2 + ch) * 128 + row] = best;
+      cand_i[(tb * 2 + ch) * 128 + row] = besti;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&cand_full[tb]);                      // (mbarrier.arrive has release semantics)
+    }
   } else {
-    // ===================================================== epilogue: thread = one point (TMEM lane)
-    const int quad = warp & 3;                                         // TMEM lanes [32 quad, 32 quad + 32)
-    const int row = quad * 32 + lane;                                  // point within the tile
-    const int et = threadIdx.x - 64;                                   // 0..127 among epilogue threads
+    // ===================================================== finisher warps: 2 groups x 4 warps; group f takes tiles with parity f.
+    // Merge the two column halves, recompute the winner's similarity exactly in fp32, store, release the A stage.
+    const int f = (warp - 10) >> 2;
+    const int row = ((warp - 10) & 3) * 32 + lane;
     int cur_l = -1; uint32_t bgen = 0;
     long long it = 0;
     for (long long t = t_begin; t < t_end; ++t, ++it) {
       const int li = (int)(t / P.tiles_per_l), ti = (int)(t % P.tiles_per_l);
-      const int s = (int)(it % TC_STAGES);
-      const int tb = (int)(it & 1); const uint32_t tph = (uint32_t)(it >> 1) & 1;
-      if (li != cur_l) {
-        // |c_j|^2 of the new centroid set, from the B tile in shared memory (2 columns per thread)
-        mbar_wait(b_full, bgen & 1); ++bgen; cur_l = li;
-        asm volatile("bar.sync 1, 128;" ::: "memory");                // nobody still reads the old c2
-        for (int j = et; j < 256; j += 128) {
-          float s2 = 0.f;
-          if (j < P.kpad) {
-            const uint8_t* bj = sB + (j >> 5) * box_bytes;
-            for (int e = 0; e < d; ++e) { const float v = *reinterpret_cast<const float*>(bj + box_off(e, j & 31)); s2 = fmaf(v, v, s2); }
-          }
-          c2[j] = (j < P.k) ? s2 : INFINITY;                           // padded columns can never win
+      const bool last_of_l = (t + 1 == t_end) || ((int)((t + 1) / P.tiles_per_l) != li);
+      if (li != cur_l) { mbar_wait(b_full, bgen & 1); ++bgen; cur_l = li; }   // B tile of this k-means is in shared memory
+      const int tb = (int)(it & 1);
+      if (tb == f) {
+        const int s = (int)(it % TC_STAGES); const uint32_t tph = (uint32_t)(it >> 1) & 1;
+        mbar_wait(&cand_full[tb], tph);
+        float best = cand_v[(tb * 2 + 0) * 128 + row]; int besti = cand_i[(tb * 2 + 0) * 128 + row];
+        const float ov = cand_v[(tb * 2 + 1) * 128 + row]; const int oi = cand_i[(tb * 2 + 1) * 128 + row];
+        if (ov > best) { best = ov; besti = oi; }                      // halves ascend in column index: '>' keeps the lowest
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cand_empty[tb]);
+        // exact fp32 similarity of the chosen centroid (max_sim.cu:78-98 arithmetic)
+        const uint8_t* xa = sA + s * (size_t)a_bytes + (row >> 5) * box_bytes;
+        const uint8_t* cb = sB + (besti >> 5) * box_bytes;
+        float acc = 0.f;
+        #pragma unroll 8
+        for (int e = 0; e < d; ++e) {
+          const float xv = *reinterpret_cast<const float*>(xa + box_off(e, row & 31));
+          const float cvv = *reinterpret_cast<const float*>(cb + box_off(e, besti & 31));
+          const float dif = xv - cvv;
+          acc = fmaf(-dif, dif, acc);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      mbar_wait(&tmem_full[tb], tph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float best = -INFINITY; int besti = 0;
-      for (int c0 = 0; c0 < P.kpad; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tb * 256 + c0), v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float sc = fmaf(2.f, __uint_as_float(v[j]), -c2[c0 + j]);
-          if (sc > best) { best = sc; besti = c0 + j; }                // strict '>' keeps the lowest index on ties
+        const long long p = (long long)ti * TC_M + row;
+        if (p < P.n) {
+          P.maxsims[(size_t)li * P.n + p] = acc;
+          P.labels[(size_t)li * P.n + p] = besti;
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_a[s]);                       // this warp is done reading the A stage
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      if (lane == 0) mbar_arrive(&tmem_empty[tb]);
-      // exact fp32 similarity of the chosen centroid (max_sim.cu:78-98 arithmetic)
-      const uint8_t* xa = sA + s * (size_t)a_bytes + (row >> 5) * box_bytes;
-      const uint8_t* cb = sB + (besti >> 5) * box_bytes;
-      float acc = 0.f;
-      for (int e = 0; e < d; ++e) {
-        const float xv = *reinterpret_cast<const float*>(xa + box_off(e, row & 31));
-        const float cv = *reinterpret_cast<const float*>(cb + box_off(e, besti & 31));
-        const float dif = xv - cv;
-        acc = fmaf(-dif, dif, acc);
-      }
-      const long long p = (long long)ti * TC_M + row;
-      if (p < P.n) {
-        P.maxsims[(size_t)li * P.n + p] = acc;
-        P.labels[(size_t)li * P.n + p] = besti;
-      }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&empty_a[s]);                                      // this warp is done reading the A stage
-        const bool last_of_l = (t + 1 == t_end) || ((int)((t + 1) / P.tiles_per_l) != li);
-        if (last_of_l) mbar_arrive(b_free);                            // ... and, for this k-means, the B tile
+      if (last_of_l) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_free);                            // done with this k-means' B tile (both groups arrive)
       }
     }
   }
@@ -284,7 +359,7 @@ static int make_map(CUtensorMap* map, const float* base, int l, int rows, long l
   cuuint32_t box[3] = {32, (cuuint32_t)rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return TPQ_ERR_CUDA; }
   return TPQ_OK;
@@ -304,9 +379,9 @@ int launch_assign_tc(const float* data, const float* cent, int l, int d, long lo
   TcParams P;
   P.l = l; P.d = d; P.n = (int)n; P.k = k; P.kpad = (k + 31) / 32 * 32;
   P.tiles_per_l = (int)((n + TC_M - 1) / TC_M);
-  P.maxsims = maxsims; P.labels = labels; P.cent = cent;
+  P.maxsims = maxsims; P.labels = labels; P.cent = cent; P.dbg = g_tc_dbg;
   const size_t box = (size_t)d * 128;
-  const size_t smem = (size_t)(P.kpad / 32) * box + (size_t)TC_STAGES * 4 * box + 256 * 4 + 32 * 8 + 1024;
+  const size_t smem = (size_t)(P.kpad / 32) * box + (size_t)TC_STAGES * 4 * box + 12 * 1024 + 256 * 4 + 32 * 8 + 8192 + 1024;
   TPQ_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -319,3 +394,5 @@ int launch_assign_tc(const float* data, const float* cent, int l, int d, long lo
 }
 
 }  // namespace tpq
+
+extern "C" void tpq_debug_set_tc_dump(float* p) { tpq::g_tc_dbg = p; }
