@@ -31,11 +31,18 @@ if "c5" in which or "centroids" in which:
     data = torch.randn(l, d, n, device=dev)
     cent = data[:, :, :k].contiguous()
     if "c5" in which:
-        ms = timeit(lambda: T.fn.max_sim(data, cent), reps=3, warm=1)
         byts = 4 * l * d * n + 4 * l * d * k + 12 * l * n
-        out["c5_max_sim"] = {"ms": ms, "algorithmic_GB": byts / 1e9, "GBps": byts / ms / 1e6, "frac_of_hbm_peak": byts / ms / 1e6 / peak,
-                             "tflops_gemm_form": 2.0 * l * n * d * k / ms / 1e9, "kernel": "max_sim_kernel (fp32 SIMT, exact)"}
-        print(out["c5_max_sim"], flush=True)
+        for exact, name, kern in ((False, "c5_max_sim_tc", "assign_tc_kernel (tcgen05 TF32 + exact fp32 maxsim)"),
+                                  (True, "c5_max_sim_exact", "max_sim_kernel (fp32 SIMT, exact)")):
+            if exact and "c5fast" in which:
+                continue
+            ms = timeit(lambda: T.fn.max_sim(data, cent, exact=exact), reps=3, warm=1)
+            out[name] = {"ms": ms, "algorithmic_GB": byts / 1e9, "GBps": byts / ms / 1e6, "frac_of_hbm_peak": byts / ms / 1e6 / peak,
+                         "tflops_gemm_form": 2.0 * l * n * d * k / ms / 1e9, "kernel": kern}
+            print(out[name], flush=True)
+        lt = T.fn.max_sim(data[:2], cent[:2], exact=False)[1]
+        le = T.fn.max_sim(data[:2], cent[:2], exact=True)[1]
+        out["c5_label_agreement_tc_vs_exact"] = float((lt == le).float().mean())
     if "centroids" in which:
         lab = T.fn.max_sim(data, cent)[1]
         ms = timeit(lambda: T.fn.compute_centroids(data, lab, k), reps=3, warm=1)

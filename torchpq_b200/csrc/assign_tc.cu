@@ -17,7 +17,11 @@
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 = arg-max
 // over the TMEM accumulator (4 lane quadrants x 2 column halves), warps 10..17 = finishers (exact similarity + stores),
-// two groups alternating tiles so the dependent fp32 chain of one tile overlaps the next tile's arg-max.  Three pipelines: A stages (TMA -> MMA + epilogue), the
+// two groups alternating tiles so the dependent fp32 chain of one tile overlaps the next tile's arg-max.
+//
+// Bound (measured, profiles/r01_assign_tc_raw.csv): the arg-max must read every accumulator back, n*k*4 bytes of
+// TMEM reads (C5: 65 GB) against ~64 B/clk/SM of tcgen05.ld bandwidth = ~3.6 ms; the HBM stream (17.2 GB) would
+// take 2.65 ms.  Round 1 reaches 5.6 ms (3.0 TB/s of HBM traffic, tensor pipe 38 % busy).  Three pipelines: A stages (TMA -> MMA + epilogue), the
 // resident B tile (reloaded when the CTA's tile range crosses into the next k-means), two TMEM accumulators.
 #include <cuda.h>
 #include "common.cuh"
@@ -25,7 +29,7 @@
 namespace tpq {
 
 constexpr int TC_M = 128;          // points per tile
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 4;
 constexpr int TC_THREADS = 64 + 512;
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -303,15 +307,23 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&cand_empty[tb]);
         // exact fp32 similarity of the chosen centroid (max_sim.cu:78-98 arithmetic)
+        // The swizzle term of box_off has period 4 in the row: four precomputed bases per operand, the row offset
+        // (e * 128) folds into the load's immediate after unrolling -> 2 LDS + FADD + FFMA per feature.
         const uint8_t* xa = sA + s * (size_t)a_bytes + (row >> 5) * box_bytes;
         const uint8_t* cb = sB + (besti >> 5) * box_bytes;
+        const uint8_t* xq[4]; const uint8_t* cq[4];
+        #pragma unroll
+        for (int r = 0; r < 4; ++r) { xq[r] = xa + box_off(r, row & 31); cq[r] = cb + box_off(r, besti & 31); }
         float acc = 0.f;
-        #pragma unroll 8
-        for (int e = 0; e < d; ++e) {
-          const float xv = *reinterpret_cast<const float*>(xa + box_off(e, row & 31));
-          const float cvv = *reinterpret_cast<const float*>(cb + box_off(e, besti & 31));
-          const float dif = xv - cvv;
-          acc = fmaf(-dif, dif, acc);
+        #pragma unroll 2
+        for (int e4 = 0; e4 < d; e4 += 4) {
+          #pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float xv = *reinterpret_cast<const float*>(xq[r] + e4 * 128);
+            const float cvv = *reinterpret_cast<const float*>(cq[r] + e4 * 128);
+            const float dif = xv - cvv;
+            acc = fmaf(-dif, dif, acc);
+          }
         }
         const long long p = (long long)ti * TC_M + row;
         if (p < P.n) {
