@@ -133,6 +133,22 @@ struct WarpTopK {
   }
 };
 
+// Bitonic sort of a[0..n) (n a power of two), DESCENDING, by the whole CTA (every thread must call it).
+__device__ __forceinline__ void cta_sort_desc(uint64_t* a, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+        int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        int hi = lo + j;
+        bool desc = ((lo & k) == 0);
+        uint64_t x = a[lo], y = a[hi];
+        if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // CTA-wide top-k selector: ONE sorted list of kp keys shared by all warps of the CTA (so its
 // k-th entry is the true running k-th best of everything merged so far), one staging buffer
 // per warp.  A warp whose buffer is more than half full sorts it privately, then takes the
@@ -181,6 +197,22 @@ struct CtaTopK {
     cnt += __popc(m);
     __syncwarp();
     if (cnt > kTopkBuf - 32) flush(lane);
+  }
+  // Whole-CTA flush (every thread calls it): the staging buffers of all warps (`bufs`, nw * kTopkBuf entries,
+  // contiguous, a power of two in total) are sorted together by the CTA and merged into the list once, instead of
+  // nw lock-serialised warp flushes.  Used to bootstrap the threshold and to drain the buffers at the end.
+  __device__ __forceinline__ void cta_flush(uint64_t* bufs, int nw, int lane, int warp) {
+    for (int i = cnt + lane; i < kTopkBuf; i += 32) buf[i] = 0;   // pad this warp's unused slots
+    __syncthreads();
+    const int nb = nw * kTopkBuf;
+    cta_sort_desc(bufs, nb);
+    if (warp == 0) {
+      const int take = nb < kp ? nb : kp;
+      warp_merge_desc(list, kp, bufs, take, lane);
+      if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(thr) = list[k - 1];
+    }
+    cnt = 0;
+    __syncthreads();
   }
 };
 #endif  // __CUDACC__

@@ -181,6 +181,22 @@ struct Scanner {
     tk.push(live && key > thr, key, lane);
     B_cur = B_nxt; a0_cur = a0_nxt; valid_cur = valid_nxt;
   }
+  template <int SB>
+  __device__ __forceinline__ void simple_units(float (&acc)[4], int64_t B) {
+    load_unit<MP, SB>(regs[0], codes, B, lane);
+    adc_unit<MP, SB>(regs[0], off, lut, acc);
+    if constexpr (SB + 1 < NSB) simple_units<SB + 1>(acc, B);
+  }
+  // score one block without pipelining and return this lane's key (0 if the slot is not live)
+  __device__ __forceinline__ uint64_t key_of_block(int b) {
+    int64_t B; uint32_t a0;
+    locate(b, B, a0);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    simple_units<0>(acc, B);
+    const uint32_t v = __ldg(valid + B);
+    const float score = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    return ((v >> lane) & 1u) ? make_key(score, a0 + lane) : 0ull;
+  }
   __device__ __forceinline__ void run(int b, int b_end) {
     if (b >= b_end) return;
     locate(b, B_cur, a0_cur);
@@ -247,6 +263,32 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   const int q = A.q_base + qi;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  // --- probe segments first (warp 0): their dependent global loads overlap the other warps' LUT work (same visiting rules as scan_ref.cu / ivfpq_topk.cu:837-870)
+  int P = (int)A.n_probe_list[q];
+  P = max(1, min(P, A.n_probe));
+  if (warp == 0) {
+    int carry = 0;
+    if (lane == 0) seg_prefix[0] = 0;
+    const int64_t* cq = A.cells + (size_t)q * A.n_probe;
+    for (int j0 = 0; j0 < P; j0 += 32) {
+      const int j = j0 + lane;
+      int nb = 0;
+      if (j < P) {
+        const int64_t c = cq[j];
+        const int64_t s = A.cell_start[c];
+        const bool skip = (j > 0) && (s == A.cell_start[cq[j - 1]]);
+        const int b0 = A.cell_block_start[c];
+        nb = skip ? 0 : A.cell_block_start[c + 1] - b0;
+        seg_blk0[j] = b0;
+        seg_addr0[j] = (uint32_t)s;
+      }
+      int incl = nb;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (j < P) seg_prefix[j + 1] = carry + incl;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
   if constexpr (DSUB == 0) {
     // --- stage LUT (MG * 64 KB, coalesced 16-byte copies)
     const float4* src = reinterpret_cast<const float4*>(A.lut_scan + (size_t)qi * MG * 16384);
@@ -290,32 +332,6 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       }
     }
   }
-  // --- probe segments (same visiting rules as scan_ref.cu / ivfpq_topk.cu:837-870)
-  int P = (int)A.n_probe_list[q];
-  P = max(1, min(P, A.n_probe));
-  if (warp == 0) {
-    int carry = 0;
-    if (lane == 0) seg_prefix[0] = 0;
-    const int64_t* cq = A.cells + (size_t)q * A.n_probe;
-    for (int j0 = 0; j0 < P; j0 += 32) {
-      const int j = j0 + lane;
-      int nb = 0;
-      if (j < P) {
-        const int64_t c = cq[j];
-        const int64_t s = A.cell_start[c];
-        const bool skip = (j > 0) && (s == A.cell_start[cq[j - 1]]);
-        const int b0 = A.cell_block_start[c];
-        nb = skip ? 0 : A.cell_block_start[c + 1] - b0;
-        seg_blk0[j] = b0;
-        seg_addr0[j] = (uint32_t)s;
-      }
-      int incl = nb;
-      #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      if (j < P) seg_prefix[j + 1] = carry + incl;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-  }
   Scanner<MP, NW> sc;
   sc.codes = A.codes; sc.valid = A.valid; sc.lut = lut;
   sc.seg_prefix = seg_prefix; sc.seg_blk0 = seg_blk0; sc.seg_addr0 = seg_addr0; sc.lane = lane;
@@ -337,10 +353,21 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   const int b_end = (int)(((int64_t)total * (slice + 1)) / A.S);
   sc.thr = 0;
   sc.seg = 0; sc.seg_lo = 0; sc.seg_hi = seg_prefix[1]; sc.seg_b0 = seg_blk0[0]; sc.seg_a0 = seg_addr0[0];
-  sc.run(b_begin + warp, b_end);
   CtaTopK& tk = sc.tk;
-  tk.flush(lane);
-  __syncthreads();
+  uint64_t* bufs = reinterpret_cast<uint64_t*>(smem + L.bufs);
+  // bootstrap: the first two blocks of every warp go to the list unfiltered through ONE CTA-wide sort, which
+  // establishes the threshold (k-th best of the first NW * 64 vectors) without 2 * NW lock-serialised flushes
+  {
+    #pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+      const int b = b_begin + warp + r * NW;
+      tk.buf[r * 32 + lane] = (b < b_end) ? sc.key_of_block(b) : 0ull;
+    }
+    tk.cnt = kTopkBuf;
+    tk.cta_flush(bufs, NW, lane, warp);
+  }
+  sc.run(b_begin + warp + 2 * NW, b_end);
+  tk.cta_flush(bufs, NW, lane, warp);                          // drain every warp's staging buffer with one CTA-wide sort
   uint64_t* out = A.keys_out + ((size_t)q * A.S + slice) * A.k;
   for (int i = tid; i < A.k; i += NW * 32) out[i] = tk.list[i];
 }
