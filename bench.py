@@ -250,17 +250,37 @@ def main():
             return tdist.sharded_search(index, x, k)
         return index.search(x, k=k)
 
-    out_v = torch.empty(nq, k, dtype=torch.float32).pin_memory()
-    out_i = torch.empty(nq, k, dtype=torch.long).pin_memory()
-    x_in = torch.empty(d, nq, dtype=torch.float32, device=device)
+    # end-to-end leg: host (pinned) queries in, host (pinned) results out, every step.  Copies run on their own
+    # stream with double-buffered staging tensors, so step i's D2H and step i+1's H2D overlap step i+1's search --
+    # all of it inside the timed region.
+    copy_stream = torch.cuda.Stream(device)
+    out_v = [torch.empty(nq, k, dtype=torch.float32).pin_memory() for _ in range(2)]
+    out_i = [torch.empty(nq, k, dtype=torch.long).pin_memory() for _ in range(2)]
+    x_in = [torch.empty(d, nq, dtype=torch.float32, device=device) for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    res = [None, None]
 
     def step_e2e(i):
-        x_in.copy_(xs_host[i % len(xs_host)], non_blocking=True)
+        b = i & 1
+        main = torch.cuda.current_stream(device)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[b])                       # search i-2 no longer reads x_in[b]
+            x_in[b].copy_(xs_host[i % len(xs_host)], non_blocking=True)
+            ev_in[b].record(copy_stream)
+        main.wait_event(ev_in[b])
         if world > 1:
-            v, ids = tdist.sharded_search(index, x_in, k)
+            v, ids = tdist.sharded_search(index, x_in[b], k)
         else:
-            v, ids = index.search(x_in, k=k)
-        out_v.copy_(v, non_blocking=True); out_i.copy_(ids, non_blocking=True)
+            v, ids = index.search(x_in[b], k=k)
+        ev_free[b].record(main)
+        ev_done[b].record(main)
+        res[b] = (v, ids)                                            # keep alive until the copy stream has read them
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_done[b])
+            out_v[b].copy_(v, non_blocking=True); out_i[b].copy_(ids, non_blocking=True)
+            v.record_stream(copy_stream); ids.record_stream(copy_stream)
 
     def barrier():
         if world > 1:
@@ -273,6 +293,7 @@ def main():
         e0.record()
         for i in range(steps):
             fn(i)
+        torch.cuda.current_stream(device).wait_stream(copy_stream) if fn is step_e2e else None
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)

@@ -7,15 +7,17 @@ import bench
 import torchpq_b200 as T
 
 wl_name = sys.argv[1] if len(sys.argv) > 1 else "c3"
+shard = int(os.environ.get("SHARD_WORLD", "1"))          # emulate one rank of a cell-sharded index on this GPU
 cfgs = sys.argv[2:] or ["8x2", "8x3", "12x2", "16x1", "4x4", "4x6"]
 wl = bench.WORKLOADS[wl_name]
 dev = torch.device("cuda:0")
 index, base = bench.build_index(wl, dev)
 del base
+index.set_shard(0, shard)
 k = wl[5]
 xs = [x.to(dev) for x in bench.gen_queries(wl[1], 10000, 4, dev)]
 lib = T._lib.lib
-for smart in (True, False):
+for smart in (True,):
     index.use_smart_probing = smart
     for cfg in cfgs:
         os.environ["TPQ_SCAN_CFG"] = cfg

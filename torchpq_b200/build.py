@@ -21,10 +21,12 @@ from __future__ import annotations
 import torch
 
 
-def _assign(data: torch.Tensor, cent: torch.Tensor) -> torch.Tensor:
-    """data [l, d, n], cent [l, d, k] -> labels [l, n] int64: tpq_max_sim (exact -sum (x-c)^2, lowest index on ties)."""
+def _assign(data: torch.Tensor, cent: torch.Tensor, exact: bool = True) -> torch.Tensor:
+    """data [l, d, n], cent [l, d, k] -> labels [l, n] int64: tpq_max_sim.  exact=True: the reference's fp32
+    arithmetic (used for encoding, so codes match the reference's); exact=False: TF32 tensor-core kernel where it
+    applies (used inside the Lloyd iterations, where a label flip between near-equidistant centroids is harmless)."""
     from . import fn
-    return fn.max_sim(data.contiguous(), cent.contiguous(), "euclidean")[1]
+    return fn.max_sim(data.contiguous(), cent.contiguous(), "euclidean", exact=exact)[1]
 
 
 def multi_kmeans(data: torch.Tensor, k: int, max_iter: int, tol: float = 1e-4, seed: int = 0) -> torch.Tensor:
@@ -37,7 +39,7 @@ def multi_kmeans(data: torch.Tensor, k: int, max_iter: int, tol: float = 1e-4, s
         cent = torch.cat([cent, torch.zeros(l, d, k - cent.shape[2], device=data.device)], dim=2)
     from . import fn
     for _ in range(max_iter):
-        lab = _assign(data, cent)
+        lab = _assign(data, cent, exact=False)
         new = fn.compute_centroids(data, lab, k)
         shift = (new - cent).pow(2).sum(dim=1).sqrt().mean()
         cent = new

@@ -133,11 +133,17 @@ probe_select_kernel(const float* __restrict__ sims, int nq, int C, int n_probe, 
   tk.init(base, base + kp, kp, n_probe, lane);
   const float* row = sims + (size_t)q * C;
   uint64_t thr = 0;
-  for (int c0 = 0; c0 < C; c0 += 32) {
-    int c = c0 + lane;
-    bool ok = c < C;
-    uint64_t key = ok ? make_key(row[c], (uint32_t)c) : 0ull;
-    if (tk.push(ok && key > thr, key, lane)) thr = tk.kth();
+  for (int c0 = 0; c0 < C; c0 += 128) {                  // four loads in flight per lane
+    float v[4];
+    #pragma unroll
+    for (int u = 0; u < 4; ++u) { const int c = c0 + u * 32 + lane; v[u] = c < C ? __ldg(row + c) : 0.f; }
+    #pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * 32 + lane;
+      const bool ok = c < C;
+      const uint64_t key = ok ? make_key(v[u], (uint32_t)c) : 0ull;
+      if (tk.push(ok && key > thr, key, lane)) thr = tk.kth();
+    }
   }
   tk.flush(lane);
   float* ps = probe_sims + (size_t)q * n_probe;

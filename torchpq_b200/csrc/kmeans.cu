@@ -128,6 +128,74 @@ centroid_accumulate_kernel(const float* __restrict__ data, const int64_t* __rest
     for (int j = tid; j < k; j += blockDim.x) if (cnt[j] != 0.f) atomicAdd(counts + (size_t)l * k + j, cnt[j]);
 }
 
+// Same update for k <= 1024 without one shared-memory atomic per element: the tile's points are counting-sorted
+// by label once (permutation in shared memory), then for every feature the row is staged in shared memory and each
+// warp sums whole label segments with contiguous permutation reads + a shuffle reduction; only the per-(feature,
+// cluster) partial of the tile goes to global memory.  tile = CS_T points, one CTA per (tile, l).
+constexpr int CS_T = 8192;
+__global__ void __launch_bounds__(512)
+centroid_sorted_kernel(const float* __restrict__ data, const int64_t* __restrict__ labels,
+                       int d, int n, int k, float* __restrict__ sums, float* __restrict__ counts) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  float* xrow = reinterpret_cast<float*>(sm);                       // [CS_T]
+  uint16_t* perm = reinterpret_cast<uint16_t*>(xrow + CS_T);        // [CS_T] point (within tile) at sorted position
+  uint16_t* lab16 = perm + CS_T;                                    // [CS_T]
+  int* seg = reinterpret_cast<int*>(lab16 + CS_T);                  // [k + 1] segment starts
+  int* cur = seg + (k + 1);                                         // [k] scatter cursors / histogram
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int l = blockIdx.y, n0 = blockIdx.x * CS_T, np = min(CS_T, n - n0);
+  for (int j = tid; j < k; j += blockDim.x) cur[j] = 0;
+  __syncthreads();
+  const int64_t* lab = labels + (size_t)l * n + n0;
+  for (int p = tid; p < np; p += blockDim.x) {
+    int j = (int)lab[p];
+    j = (j >= 0 && j < k) ? j : 0xFFFF;                              // out-of-range labels are ignored (as the reference does)
+    lab16[p] = (uint16_t)j;
+    if (j != 0xFFFF) atomicAdd(&cur[j], 1);
+  }
+  __syncthreads();
+  if (warp == 0) {                                                   // exclusive scan of the histogram
+    int carry = 0;
+    for (int j0 = 0; j0 < k; j0 += 32) {
+      const int j = j0 + lane;
+      const int c = j < k ? cur[j] : 0;
+      int incl = c;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (j < k) { seg[j] = carry + incl - c; }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) seg[k] = carry;
+  }
+  __syncthreads();
+  for (int j = tid; j < k; j += blockDim.x) {
+    const int c = cur[j];
+    if (c) atomicAdd(counts + (size_t)l * k + j, (float)c);
+    cur[j] = seg[j];
+  }
+  __syncthreads();
+  for (int p = tid; p < np; p += blockDim.x) {
+    const int j = lab16[p];
+    if (j != 0xFFFF) perm[atomicAdd(&cur[j], 1)] = (uint16_t)p;
+  }
+  __syncthreads();
+  for (int e = 0; e < d; ++e) {
+    const float* x = data + ((size_t)l * d + e) * n + n0;
+    for (int p = tid; p < np; p += blockDim.x) xrow[p] = x[p];
+    __syncthreads();
+    for (int j = warp; j < k; j += nw) {
+      const int s0 = seg[j], s1 = seg[j + 1];
+      if (s1 == s0) continue;
+      float acc = 0.f;
+      for (int i = s0 + lane; i < s1; i += 32) acc += xrow[perm[i]];
+      #pragma unroll
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) atomicAdd(sums + ((size_t)l * d + e) * k + j, acc);
+    }
+    __syncthreads();
+  }
+}
+
 // centroids = count == 0 ? 0 : sum / count   (compute_centroids.cu:80)
 __global__ void centroid_finalize_kernel(float* __restrict__ cent, const float* __restrict__ counts, int d, int k, size_t total) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,7 +274,13 @@ extern "C" int tpq_compute_centroids(const float* data, const int64_t* labels, i
   float* counts = reinterpret_cast<float*>(ws);
   TPQ_CUDA(cudaMemsetAsync(centroids, 0, (size_t)l * d * k * 4, st));
   TPQ_CUDA(cudaMemsetAsync(counts, 0, (size_t)l * k * 4, st));
-  if (n > 0) {
+  if (n > 0 && k <= 1024) {
+    const size_t smem = (size_t)CS_T * 4 + (size_t)CS_T * 2 * 2 + (size_t)(2 * k + 1) * 4;
+    TPQ_CUDA(cudaFuncSetAttribute(centroid_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((n + CS_T - 1) / CS_T), l);
+    centroid_sorted_kernel<<<grid, 512, smem, st>>>(data, labels, d, (int)n, k, centroids, counts);
+    TPQ_LAUNCH_CHECK("centroid_sorted_kernel");
+  } else if (n > 0) {
     int de = (int)((160 * 1024 / 4 - k) / k);               // features per CTA so that (de+1)*k floats fit 160 KB
     if (de < 1) { set_error("tpq_compute_centroids: k=%d too large for one shared-memory row set", k); return TPQ_ERR_UNSUPPORTED; }
     if (de > d) de = d;

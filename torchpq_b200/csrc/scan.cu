@@ -540,14 +540,18 @@ static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cel
   if (cfg && ix->m_pad == 64) {
     if (!strcmp(cfg, "8x2"))  return launch_scan<64, 8, 2>(TPQ_SCAN_ARGS);
     if (!strcmp(cfg, "8x3"))  return launch_scan<64, 8, 3>(TPQ_SCAN_ARGS);
-    if (!strcmp(cfg, "12x2")) return launch_scan<64, 12, 2>(TPQ_SCAN_ARGS);
     if (!strcmp(cfg, "16x1")) return launch_scan<64, 16, 1>(TPQ_SCAN_ARGS);
     if (!strcmp(cfg, "4x4"))  return launch_scan<64, 4, 4>(TPQ_SCAN_ARGS);
-    if (!strcmp(cfg, "4x6"))  return launch_scan<64, 4, 6>(TPQ_SCAN_ARGS);
   }
   switch (ix->m_pad) {
     case 32:  return launch_scan<32, 8, 2>(TPQ_SCAN_ARGS);
-    case 64:  return launch_scan<64, 8, 2>(TPQ_SCAN_ARGS);
+    case 64: {
+      // Long probe lists: 2 CTAs/SM with a deep prefetch (127 registers).  Short ones (small cells, or one shard of a
+      // cell-sharded index): per-CTA prologue/epilogue weighs more, so 3 lighter CTAs/SM overlap them better
+      // (measured on C3: 1 shard 11.0 vs 11.3 ms, 1/8 shard 2.57 vs 2.11 ms).
+      const double blocks_per_cta = (double)ix->n_blocks / ix->n_cells * n_probe / S;
+      return blocks_per_cta >= 2000.0 ? launch_scan<64, 8, 2>(TPQ_SCAN_ARGS) : launch_scan<64, 8, 3>(TPQ_SCAN_ARGS);
+    }
     case 96:  return launch_scan<96, 16, 1>(TPQ_SCAN_ARGS);      // LUT >= 128 KB: one CTA per SM, so twice the warps
     case 128: return launch_scan<128, 16, 1>(TPQ_SCAN_ARGS);
     case 160: return launch_scan<160, 16, 1>(TPQ_SCAN_ARGS);
