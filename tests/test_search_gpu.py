@@ -199,3 +199,28 @@ def test_train_add_search_end_to_end(cuda_device):
     assert_close_results(v.cpu().numpy(), i.cpu().numpy(), ov, oi, rtol=1e-3, min_overlap=0.995)
     truth = O.exact_topk(base.cpu(), x.cpu(), 10, "euclidean").numpy()
     assert abs(O.recall_at_k(i.cpu().numpy(), truth) - O.recall_at_k(oi, truth)) <= 1e-3
+
+
+def test_remove_then_search_and_refill(cuda_device):
+    """remove() makes holes the scan skips; results equal the oracle on the same (holed) state; the next add
+    refills the holes first (CellContainer.add placement rule)."""
+    import torchpq_b200 as T
+    import bench
+    torch.manual_seed(2)
+    base = torch.randn(32, 6000, device="cuda")
+    ix = T.IVFPQIndex(32, 8, 16, initial_size=512, device="cuda:0")
+    ix.train(base[:, :3000].contiguous())
+    ids = ix.add(base)
+    gone = ids[::7]
+    adr_gone = ix.get_address_by_id(gone)
+    ix.remove(ids=gone)
+    assert ix.n_items == 6000 - gone.shape[0]
+    assert (ix.get_address_by_id(gone) == -1).all()
+    ix.n_probe = 8
+    x = torch.randn(32, 64, device="cuda")
+    v, i = ix.search(x, k=20)
+    assert not torch.isin(i, gone).any()
+    ov, oi = O.search(bench.to_oracle_state(ix), x.cpu(), k=20)
+    assert_close_results(v.cpu().numpy(), i.cpu().numpy(), ov, oi, rtol=1e-3, min_overlap=0.995)
+    new_ids, new_adr = ix.add(base[:, :200].contiguous(), return_address=True)
+    assert torch.isin(new_adr, adr_gone).all()            # holes are reused before fresh slots

@@ -22,11 +22,41 @@ def merge_gathered(keys_all: torch.Tensor, address2id: torch.Tensor):
     return fn.merge_topk(keys_all.contiguous(), address2id)
 
 
-def sharded_search(index, x: torch.Tensor, k: int, group=None, return_address: bool = False):
+def _gather_rows(t: torch.Tensor, world: int, group):
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+def sharded_search(index, x: torch.Tensor, k: int, group=None, return_address: bool = False,
+                   split_coarse: bool = True):
     """``index`` holds the full reference state on every rank and has been given its shard with
-    ``index.set_shard(rank, world)``.  Returns the same (values, ids[, address]) on every rank."""
+    ``index.set_shard(rank, world)``.  Returns the same (values, ids[, address]) on every rank.
+
+    split_coarse (default): the coarse probe -- the one stage that does not shrink with the shard -- is itself split
+    by QUERIES: rank r probes queries [r*nq/world, (r+1)*nq/world) and a small all-gather (n_probe+1 int64 per query)
+    hands every rank the full probe lists.  Same deterministic kernel on every rank, so the lists are bit-identical
+    to the replicated computation.  split_coarse=False runs the whole coarse probe on every rank (one collective
+    per batch in total instead of two)."""
     world = dist.get_world_size(group)
-    _, _, keys = index.search(x, k=k, return_keys=True)
+    rank = dist.get_rank(group)
+    if world > 1 and split_coarse:
+        nq, n_probe = x.shape[1], int(index.n_probe)
+        xq = fn.normalize(x.contiguous()) if index.distance == "cosine" else x.contiguous()   # IVFPQIndex.py:474-475
+        per = (nq + world - 1) // world
+        lo = min(nq, rank * per)
+        hi = min(nq, lo + per)
+        mine = torch.zeros(per, n_probe + 1, dtype=torch.long, device=x.device)
+        if hi > lo:
+            _, cells, npl = fn.coarse_probe(xq[:, lo:hi].contiguous(), index.vq_codec.codebook, n_probe,
+                                            index.use_smart_probing, index.smart_probing_temperature)
+            mine[:hi - lo, :n_probe] = cells
+            mine[:hi - lo, n_probe] = npl
+        allp = _gather_rows(mine, world, group)[:nq]
+        keys = index.search_cells(xq, allp[:, :n_probe].contiguous(), n_probe_list=allp[:, n_probe].contiguous(),
+                                  k=k, return_keys=True)[2]
+    else:
+        _, _, keys = index.search(x, k=k, return_keys=True)
     if world == 1:
         keys_all = keys[None]
     else:

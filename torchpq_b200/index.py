@@ -110,6 +110,7 @@ class IVFPQIndex(StateModule):
         self.pq_codec = Codec()
         self._layout: Optional[ScanLayout] = None
         self._shard = (0, 1)
+        self._id2address_fp = None
 
     # ------------------------------------------------------------------ container properties
     @property
@@ -122,7 +123,7 @@ class IVFPQIndex(StateModule):
 
     @property
     def n_items(self):
-        return int(self._cell_size.sum().item())
+        return int((self._is_empty == 0).sum().item())               # live vectors (== _cell_size.sum() until a remove)
 
     # flags the reference exposes and this path ignores (always the fused fp32 coarse kernel)
     use_cublas = True
@@ -203,7 +204,7 @@ class IVFPQIndex(StateModule):
             out = out + (keys,)
         return out
 
-    def search_cells(self, x, cells, base_sims=None, n_probe_list=None, k=1, return_address=False):
+    def search_cells(self, x, cells, base_sims=None, n_probe_list=None, k=1, return_address=False, return_keys=False):
         """IVFPQIndex.search_cells, non-residual branch (IVFPQIndex.py:407-467)."""
         x = self._check_query(x, k)
         lay = self.layout()
@@ -217,12 +218,18 @@ class IVFPQIndex(StateModule):
         values = torch.empty(nq, k, dtype=torch.float32, device=dev)
         ids = torch.empty(nq, k, dtype=torch.long, device=dev)
         address = torch.empty(nq, k, dtype=torch.long, device=dev) if return_address else None
+        keys = torch.empty(nq, k, dtype=torch.int64, device=dev) if return_keys else None
         ws_bytes = lib.tpq_search_workspace_bytes(C.byref(lay.cindex), nq, n_probe, k)
         ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
         check(lib.tpq_ivfpq_search_cells(C.byref(lay.cindex), ptr(x), ptr(cells), ptr(n_probe_list), nq, n_probe, k,
-                                         ptr(values), ptr(ids), ptr(address), None, ptr(ws), ws_bytes,
+                                         ptr(values), ptr(ids), ptr(address), ptr(keys), ptr(ws), ws_bytes,
                                          _lib.current_stream(dev)))
-        return (values, ids, address) if return_address else (values, ids)
+        out = (values, ids)
+        if return_address:
+            out = out + (address,)
+        if return_keys:
+            out = out + (keys,)
+        return out
 
     # ------------------------------------------------------------------ build side (torch ops, see build.py)
     def train(self, x, force_retrain=False, seed=0):
@@ -235,6 +242,48 @@ class IVFPQIndex(StateModule):
     def add(self, x, ids=None, return_address=False):
         from . import build
         return build.add(self, x, ids, return_address)
+
+    def get_address_by_id(self, ids):
+        """BaseContainer.get_address_by_id with the inverse id map (BaseContainer.py:78-110; IVFPQIndex builds its
+        container with use_inverse_id_mapping=True, IVFPQIndex.py:39)."""
+        assert ids.dtype == torch.int64
+        ids = ids.to(self._address2id.device)
+        if self._id2address is None or self._id2address_fp != _fingerprint(self._address2id):
+            a2i_v, a2i_i = self._address2id.sort()
+            keep = a2i_v >= 0
+            id2a = -torch.ones(self._max_id + 1, dtype=torch.long, device=ids.device)
+            id2a[a2i_v[keep]] = a2i_i[keep]
+            delattr(self, "_id2address")
+            self.register_buffer("_id2address", id2a)
+            self._id2address_fp = _fingerprint(self._address2id)
+        mask = (0 <= ids) & (ids <= self._max_id)
+        address = torch.ones_like(ids) * -1
+        address[mask] = self._id2address[ids[mask]]
+        return address
+
+    def remove(self, ids=None, address=None):
+        """CellContainer.remove (CellContainer.py:369-393) as it is documented to behave (README.md:60-66: "virtually
+        remove vectors ... ignores ids that don't exist").  The shipped reference returns early whenever fewer items
+        are removed than the index holds (CellContainer.py:381-383), i.e. it never removes anything; that bug is not
+        reproduced.  Removed slots become holes (is_empty = 1, address2id = -1) that the scan skips and that the next
+        `add` into the cell fills first.  `_cell_size` is deliberately NOT decremented: search scans
+        [cell_start, cell_start + cell_size) (ivfpq_topk.cu:852-853), so shrinking it -- as the reference's dead code
+        would -- hides live vectors at the tail of the cell."""
+        if ids is not None:
+            address = self.get_address_by_id(ids)
+        elif address is not None:
+            assert address.dtype == torch.int64
+            address = address.to(self._address2id.device)
+        else:
+            raise RuntimeError("Need either ids or address")
+        mask = (address >= 0) & (address < self.capacity)
+        address = address[mask].unique(sorted=True)
+        address = address[self._is_empty[address] == 0]
+        if address.shape[0] == 0:
+            return
+        self._is_empty[address] = 1
+        self._address2id[address] = -1
+        self._state_changed()
 
     def encode(self, x):
         """IVFPQIndex.encode (IVFPQIndex.py:262-287): x [d_vector, n] -> PQ codes [n_subvectors, n] uint8."""
