@@ -375,7 +375,9 @@ def main():
     except Exception as e:  # the CPU leg must not take the GPU number down with it
         cpu = {"value": None, "error": repr(e)}
 
-    launches_per_step = 7 + (1 if distance == "cosine" else 0) + (1 if world > 1 else 0)
+    # our kernels per search: 2 x col_sqnorm, coarse_gemm, probe_select, ivfpq_scan, merge_topk
+    # (+ normalize_columns for cosine, + lut_scan when d/M is not 1/2/4, + the cross-shard merge when sharded)
+    launches_per_step = 6 + (1 if distance == "cosine" else 0) + (0 if (d // M) in (1, 2, 4) else 1) + (1 if world > 1 else 0)
     line = {
         "metric": "queries/sec @ recall@100, IVFPQ search", "value": qps, "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
