@@ -76,6 +76,67 @@ def build_index(wl, device, vq_iters=4, pq_iters=4):
     return index, base
 
 
+def build_state_torch(wl, device, vq_iters=4, pq_iters=4):
+    """Reference arm only: the same synthetic index built with plain torch ops (no torchpq_b200 code at all) and
+    returned as an oracle IndexState.  Seeded Lloyd with matmul arg-max assignment, placement = stable sort by cell
+    (what CellContainer.add does for one add into a fresh container, CellContainer.py:334-353)."""
+    from oracle import ivfpq_oracle as O
+    N, d, M, C, n_probe, k, distance, n_train, _ = wl
+    base = gen_base(d, N, device)
+    if distance == "cosine":
+        base = base / (base.norm(dim=0, keepdim=True) + 1e-9)
+
+    def assign(data, cent, budget=1 << 29):                              # data [l,d,n], cent [l,d,k] -> [l,n]
+        l, _, n = data.shape
+        out = torch.empty(l, n, dtype=torch.long, device=device)
+        c2 = (cent ** 2).sum(1)
+        per = max(1, budget // max(1, l * cent.shape[2]))
+        for s in range(0, n, per):
+            sim = torch.baddbmm(-c2[:, None, :], data[:, :, s:s + per].transpose(1, 2), cent, alpha=2.0)
+            out[:, s:s + per] = sim.argmax(2)
+        return out
+
+    def kmeans(data, kk, iters, seed):
+        l, dd, n = data.shape
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        cent = data[:, :, torch.randperm(n, generator=g)[:kk].to(device)].clone()
+        ones = torch.ones(l, n, device=device)
+        for _ in range(iters):
+            lab = assign(data, cent)
+            sums = torch.zeros(l, dd, kk, device=device).scatter_add_(2, lab[:, None, :].expand(l, dd, n), data)
+            cnt = torch.zeros(l, kk, device=device).scatter_add_(1, lab, ones)
+            cent = torch.where(cnt[:, None, :] > 0, sums / cnt.clamp(min=1)[:, None, :], torch.zeros((), device=device))
+        return cent
+
+    tr = base[:, :n_train].contiguous()
+    vq = kmeans(tr[None], C, vq_iters, 0)[0].contiguous()
+    pq = kmeans(tr.reshape(M, d // M, n_train).contiguous(), 256, pq_iters, 1).contiguous()
+    cells_l, codes_l = [], []
+    for s in range(0, N, 1 << 20):
+        xc = base[:, s:s + (1 << 20)].contiguous()
+        cells_l.append(assign(xc[None], vq[None])[0])
+        codes_l.append(assign(xc.reshape(M, d // M, xc.shape[1]), pq).to(torch.uint8))
+    cells, codes = torch.cat(cells_l), torch.cat(codes_l, 1)
+    counts = torch.bincount(cells, minlength=C)
+    initial = int(counts.max().item())
+    order = torch.sort(cells, stable=True).indices
+    starts = torch.arange(C, device=device) * initial
+    first = torch.cumsum(counts, 0) - counts
+    rank_in_cell = torch.empty(N, dtype=torch.long, device=device)
+    rank_in_cell[order] = torch.arange(N, device=device) - first[cells[order]]
+    adr = starts[cells] + rank_in_cell
+    cap = C * initial
+    storage = torch.zeros(M // 4, cap, 4, dtype=torch.uint8, device=device)
+    storage[:, adr] = codes.reshape(M // 4, 4, N).transpose(1, 2)
+    a2i = -torch.ones(cap, dtype=torch.long, device=device); a2i[adr] = torch.arange(N, device=device)
+    emp = torch.ones(cap, dtype=torch.uint8, device=device); emp[adr] = 0
+    c = lambda t: t.cpu().numpy()
+    return O.IndexState(d_vector=d, n_subvectors=M, n_cells=C, distance=distance, vq_codebook=c(vq), pq_codebook=c(pq),
+                        storage=c(storage), is_empty=c(emp), cell_start=c(starts), cell_size=c(counts),
+                        cell_capacity=c(torch.zeros(C, dtype=torch.long, device=device) + initial), address2id=c(a2i),
+                        max_id=N - 1, n_probe=n_probe)
+
+
 def gen_queries(d, nq, n_batches, device, seed=4321):
     g = torch.Generator(device="cpu").manual_seed(seed)
     return [torch.randn(d, nq, generator=g).pin_memory() if device.type == "cuda" else torch.randn(d, nq, generator=g)
@@ -405,14 +466,10 @@ def main():
 def run_reference(args, wl, device, threads):
     """CPU arm: the oracle restatement on the host cores; each step = a bounded query sample."""
     N, d, M, C, n_probe, k, distance, n_train, desc = wl
-    index, base = build_index(wl, device) if device.type == "cuda" else (None, None)
-    if index is None:
-        print(json.dumps({"impl": "reference", "unavailable": "no CUDA device to build the synthetic index state"}))
-        return 0
-    index.use_smart_probing = not args.no_smart
-    st = to_oracle_state(index)
-    del index, base
-    torch.cuda.empty_cache()
+    st = build_state_torch(wl, device)            # plain torch ops only; nothing of torchpq_b200 is imported on this arm
+    st.use_smart_probing = not args.no_smart
+    if device.type == "cuda":
+        torch.cuda.empty_cache()
     xs = gen_queries(d, args.nq, 1, torch.device("cpu"))[0]
     # size the per-step sample so that (steps + warmup) fit in about two minutes
     qps0, n0, used = time_oracle(st, xs, k, threads, target_s=3.0)
