@@ -224,3 +224,51 @@ def test_remove_then_search_and_refill(cuda_device):
     assert_close_results(v.cpu().numpy(), i.cpu().numpy(), ov, oi, rtol=1e-3, min_overlap=0.995)
     new_ids, new_adr = ix.add(base[:, :200].contiguous(), return_address=True)
     assert torch.isin(new_adr, adr_gone).all()            # holes are reused before fresh slots
+
+
+@pytest.mark.parametrize("M,d", [(8, 64), (12, 36), (16, 16)])
+def test_staged_lut_and_odd_subvector_sizes(cuda_device, M, d):
+    """d/M = 8, 3, 1: the LUT is staged through HBM (8, 3) or built in the scan CTA (1); all must match the oracle."""
+    st, queries = B.integer_state(d, M, 8, 3000, seed=d, lo=-4, hi=5)
+    st.n_probe, st.use_smart_probing = 5, True
+    x = queries(40)
+    ov, oi, oa = O.search(st, x, k=33, return_address=True)
+    ix = make_index(st)
+    v, i, a = ix.search(x.cuda(), k=33, return_address=True)
+    assert np.array_equal(v.cpu().numpy(), ov) and np.array_equal(a.cpu().numpy(), oa)
+
+
+def test_large_batch_is_chunked(cuda_device):
+    """nq above the library's per-launch query chunk (16384): same answers as small batches."""
+    st, queries = B.integer_state(32, 8, 8, 2000, seed=8)
+    st.n_probe, st.use_smart_probing = 3, False
+    ix = make_index(st)
+    x = queries(20000).cuda()
+    v, i = ix.search(x, k=7)
+    for s in (0, 16380, 19990):
+        v2, i2 = ix.search(x[:, s:s + 10].contiguous(), k=7)
+        assert torch.equal(v[s:s + 10], v2) and torch.equal(i[s:s + 10], i2)
+
+
+def test_many_probes_and_wide_k(cuda_device):
+    st, queries = B.integer_state(32, 8, 300, 20000, seed=13, lo=-5, hi=6)
+    st.n_probe, st.use_smart_probing = 200, True
+    x = queries(12)
+    ov, oi, oa = O.search(st, x, k=1000, return_address=True)
+    ix = make_index(st)
+    v, i, a = ix.search(x.cuda(), k=1000, return_address=True)
+    assert np.array_equal(v.cpu().numpy(), ov) and np.array_equal(a.cpu().numpy(), oa)
+
+
+def test_argument_errors(cuda_device):
+    st, queries = B.integer_state(32, 8, 8, 500, seed=1)
+    ix = make_index(st)
+    with pytest.raises(AssertionError):
+        ix.search(queries(3).cuda(), k=0)                       # IVFPQIndex.py:473
+    with pytest.raises(AssertionError):
+        ix.search(queries(3).cuda(), k=1025)
+    with pytest.raises(AssertionError):
+        ix.search(torch.zeros(31, 3, device="cuda"), k=1)       # IVFPQIndex.py:472
+    ix.n_probe = 9                                              # > n_cells
+    with pytest.raises(AssertionError):
+        ix.search(queries(3).cuda(), k=1)
