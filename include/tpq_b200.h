@@ -59,6 +59,10 @@ typedef struct tpq_index {
   const int32_t*  cell_block_start; /* [C+1] first block of each cell (exclusive prefix; [C] = n_blocks) */
   const float*    pq_codebook_t;    /* [256, m_pad, d/M] transposed PQ codebook (zero rows for padding) */
   const float*    pq_norm_t;        /* [256, m_pad] squared norms of the sub-centroids (0 for cosine) */
+  /* ---- residual IVFPQ (pq_use_residual=True, IVFPQIndex.py:48-55,160-170); NULL / 0 otherwise ---- */
+  const float*    part2_scan;       /* [C, m_pad/64 groups, 256, 64]: -2 <c_cell,m , p_m,code> - |p_m,code|^2 in LUT layout */
+  int32_t         residual;         /* 1 = codes are PQ codes of x - vq_centroid(cell) */
+  int32_t         reserved1;
 } tpq_index;
 
 /* ------------------------------------------------------------------ misc */
@@ -114,6 +118,10 @@ size_t tpq_codes_scan_bytes(int M, int64_t n_blocks);
 /* Fill codes_scan / block_valid from the reference buffers (index->storage, is_empty,
  * cell_start, cell_size) for the blocks planned in cell_block_start. */
 int tpq_relayout_codes(const tpq_index* index, uint8_t* codes_scan, uint32_t* block_valid, void* stream);
+/* Residual IVFPQ: the per-cell half of the LUT (IVFPQIndex.precompute_part2, IVFPQIndex.py:160-170) in LUT layout. */
+size_t tpq_part2_scan_bytes(int M, int n_cells);
+int tpq_relayout_part2(const float* vq_codebook, const float* pq_codebook, int d, int M, int n_cells,
+                       float* part2_scan, void* stream);
 /* Transposed PQ codebook + norms used by the in-kernel LUT build. */
 int tpq_relayout_codebook(const float* pq_codebook, int d, int M, int metric,
                           float* pq_codebook_t, float* pq_norm_t, void* stream);
@@ -130,6 +138,7 @@ int tpq_ivfpq_search(const tpq_index* index, const float* x_dn, int nq, int n_pr
 
 /* search over given probe lists (IVFPQIndex.search_cells non-residual branch, IVFPQIndex.py:407-467) */
 int tpq_ivfpq_search_cells(const tpq_index* index, const float* x_dn, const int64_t* cells,
+                           const float* base_sims /* [nq, n_probe], required when index->residual */,
                            const int64_t* n_probe_list, int nq, int n_probe, int k,
                            float* values, int64_t* ids, int64_t* address, uint64_t* keys_out,
                            void* ws, size_t ws_bytes, void* stream);

@@ -35,6 +35,19 @@ extern "C" int ref_ivfpq_topk_launch(const void* data, const float* precomputed,
       values, indices, n_data, n_query, n_probe, n_cand_pow2);
   return (int)cudaGetLastError();
 }
+// launch of IVFPQTopkCuda.topk_residual_precomputed (IVFPQTopkCuda.py:212-283)
+extern "C" int ref_ivfpq_topk_residual_precomputed_launch(
+    const void* data, const float* part1, const float* part2, const long long* cells, const float* base_sims,
+    const unsigned char* is_empty, const long long* cell_start, const long long* cell_size, const long long* tot_size,
+    const long long* n_probe_list, float* values, long long* indices,
+    int n_data, int n_query, int n_probe, int n_cand_pow2, void* stream) {
+  cudaError_t e = cudaFuncSetAttribute(ivfpq_topk_residual_precomputed, cudaFuncAttributeMaxDynamicSharedMemorySize, %(SMEM)d);
+  if (e != cudaSuccess) return (int)e;
+  ivfpq_topk_residual_precomputed<<<n_query, %(TPB)d, %(SMEM)d, (cudaStream_t)stream>>>(
+      (const uint8n_t*)data, part1, part2, cells, base_sims, is_empty, cell_start, cell_size, tot_size, n_probe_list,
+      values, indices, n_data, n_query, n_probe, n_cand_pow2);
+  return (int)cudaGetLastError();
+}
 '''
 
 

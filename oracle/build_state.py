@@ -106,3 +106,26 @@ def integer_state(d: int, n_subvectors: int, n_cells: int, n: int, seed: int = 0
         return torch.from_numpy(r.integers(lo, hi, size=(d, nq)).astype(np.float32))
 
     return st, queries
+
+
+def build_state_residual(base: torch.Tensor, n_subvectors: int, n_cells: int, seed: int = 0, n_train=None,
+                         vq_iters: int = 4, pq_iters: int = 3) -> O.IndexState:
+    """pq_use_residual=True: PQ is trained on and encodes x - vq_centroid(cell)
+    (IVFPQIndex.train :248-256, IVFPQIndex.encode :281-284)."""
+    d, n = base.shape
+    M, dsub = n_subvectors, d // n_subvectors
+    gen = torch.Generator().manual_seed(seed)
+    n_train = n if n_train is None else min(n, n_train)
+    tr = base[:, :n_train].contiguous()
+    vq = lloyd(tr, n_cells, vq_iters, gen)
+    res_tr = tr - vq[:, assign(tr, vq)]
+    sub = res_tr.reshape(M, dsub, n_train)
+    pq = torch.stack([lloyd(sub[m], 256, pq_iters, gen) for m in range(M)], 0)
+    cells = assign(base, vq)
+    res = (base - vq[:, cells]).reshape(M, dsub, n)
+    codes = np.stack([assign(res[m], pq[m]).numpy().astype(np.uint8) for m in range(M)], 0)
+    cells = cells.numpy()
+    initial = max(1, int(np.bincount(cells, minlength=n_cells).max()))
+    st = O.empty_state(d, M, n_cells, initial, "euclidean", vq.numpy().astype(np.float32), pq.numpy().astype(np.float32))
+    O.container_add(st, codes, cells)
+    return st

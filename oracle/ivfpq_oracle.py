@@ -342,3 +342,78 @@ def recall_at_k(found_ids: np.ndarray, truth_ids: np.ndarray) -> float:
     for q in range(nq):
         hit += np.intersect1d(found_ids[q], truth_ids[q]).shape[0]
     return hit / float(nq * k)
+
+
+# ----------------------------------------------------------------------------------
+# residual IVFPQ (pq_use_residual=True, precomputed part-2 tables)  --  SURVEY.md section 8(f) rank 3
+# ----------------------------------------------------------------------------------
+def precompute_part2(vq_codebook: torch.Tensor, pq_codebook: torch.Tensor) -> torch.Tensor:
+    """IVFPQIndex.precompute_part2 (IVFPQIndex.py:160-170): [M, n_cells, 256] =
+    bmm(vq^T, pq) * -2 - ||p||^2, with ||p||^2 computed as norm(dim=1).pow(2) exactly as the reference does."""
+    M, dsub, K = pq_codebook.shape
+    n_cells = vq_codebook.shape[1]
+    vq = vq_codebook.reshape(M, dsub, n_cells)
+    return torch.bmm(vq.transpose(-1, -2), pq_codebook) * -2 - pq_codebook.norm(dim=1).pow(2)[:, None]
+
+
+def residual_parts(x: torch.Tensor, vq_codebook: torch.Tensor, pq_codebook: torch.Tensor):
+    """precomputed_adc_residual_precomputed (IVFPQIndex.py:366-380):
+    part1 [nq, M, 256] = 2 * (x_m^T p_m), part2 [n_cells, M, 256] = precompute_part2^T(0,1)."""
+    M, dsub, K = pq_codebook.shape
+    nq = x.shape[1]
+    xm = x.reshape(M, dsub, nq).transpose(-1, -2)
+    part1 = 2 * (xm @ pq_codebook).permute(1, 0, 2)
+    part2 = precompute_part2(vq_codebook, pq_codebook).transpose(0, 1)
+    return part1.contiguous(), part2.contiguous()
+
+
+def ivfpq_topk_residual_precomputed(storage, part1, part2, cells, base_sims, is_empty, cell_start_g, cell_size_g,
+                                    n_probe_list, k):
+    """ivfpq_topk_residual_precomputed (ivfpq_topk.cu:1039-1207) as launched by
+    IVFPQTopkCuda.topk_residual_precomputed (IVFPQTopkCuda.py:212-283).
+    score = base_sims[q, j] + sum_m (part1[q, m, code] + part2[cell, m, code]), the smem entry being the fp32 sum
+    part1 + part2 (store_precomputed_to_smem :609-628), accumulated m ascending starting from the base similarity.
+    The loop runs over cCell < nProbe only (no unconditional first cell, unlike the non-residual kernel); an entry
+    whose start equals the previous entry's start is skipped (:1088-1104)."""
+    p1 = np.asarray(part1, np.float32); p2 = np.asarray(part2, np.float32)
+    base = np.asarray(base_sims, np.float32)
+    nq, n_probe = cell_start_g.shape
+    M = p1.shape[1]
+    as_int = np.asarray(n_probe_list).astype(np.int64).astype(np.int32).astype(np.int64)
+    P = np.clip(as_int, 0, n_probe)
+    vals = np.empty((nq, k), np.float32); adr = np.empty((nq, k), np.int64)
+    for q in range(nq):
+        sc, ad = [], []
+        prev = None
+        for j in range(int(P[q])):
+            s, n = int(cell_start_g[q, j]), int(cell_size_g[q, j])
+            if j > 0 and s == prev:
+                continue
+            prev = s
+            if n <= 0:
+                continue
+            a = np.arange(s, s + n, dtype=np.int64)
+            a = a[is_empty[a] == 0]
+            lut = (p1[q] + p2[int(cells[q, j])]).astype(np.float32)          # [M, 256]
+            codes = storage[:, a, :]
+            acc = np.full(a.shape[0], base[q, j], np.float32)
+            for m in range(M):
+                acc = acc + lut[m][codes[m // 4, :, m % 4]]
+            sc.append(acc); ad.append(a)
+        if sc:
+            vals[q], adr[q] = select_topk(np.concatenate(sc), np.concatenate(ad), k)
+        else:
+            vals[q], adr[q] = select_topk(np.zeros(0, np.float32), np.zeros(0, np.int64), k)
+    return vals, adr
+
+
+def search_residual(st: IndexState, x, k: int = 1, return_address: bool = False):
+    """IVFPQIndex.search with pq_use_residual=True and use_precomputed=True (IVFPQIndex.py:469-524, 407-438)."""
+    x = torch.as_tensor(x, dtype=torch.float32)
+    x, topk_sims, cells, npl = coarse_probe(st, x)
+    cn = cells.numpy()
+    part1, part2 = residual_parts(x, torch.from_numpy(st.vq_codebook), torch.from_numpy(st.pq_codebook))
+    vals, adr = ivfpq_topk_residual_precomputed(st.storage, part1.numpy(), part2.numpy(), cn, topk_sims.numpy(),
+                                                st.is_empty, st.cell_start[cn], st.cell_size[cn], npl.numpy(), k)
+    ids = get_id_by_address(st.address2id, adr)
+    return (vals, ids, adr) if return_address else (vals, ids)

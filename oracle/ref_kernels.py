@@ -111,3 +111,27 @@ def pq_decode(codebook, code):
     rc = lib.ref_pq_decode_launch(codebook.data_ptr(), code.data_ptr(), res.data_ptr(), m, d, n, _stream(codebook.device))
     assert rc == 0, rc
     return res.reshape(m * d, n)
+
+
+def ivfpq_topk_residual_precomputed(data, part1, part2, cells, base_sims, cell_start, cell_size, is_empty,
+                                    n_probe_list, k, tpb=256):
+    """Reference kernel `ivfpq_topk_residual_precomputed` (kernels/cuda/ivfpq_topk.cu:1039-1207) with the host logic
+    of IVFPQTopkCuda.topk_residual_precomputed (IVFPQTopkCuda.py:212-283)."""
+    m = data.shape[0] * 4
+    lib = _load(m, tpb)
+    fn = lib.ref_ivfpq_topk_residual_precomputed_launch
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 12 + [C.c_int] * 4 + [C.c_void_p]
+    n_data = data.shape[1]
+    n_query, n_probe = cell_start.shape
+    n_pow2 = 2 * (2 ** math.ceil(math.log2(math.ceil(k / 2))))
+    dev = data.device
+    tot_size = cell_size.sum(dim=1)
+    values = torch.empty(n_query, n_pow2, device=dev, dtype=torch.float32).fill_(float("-inf"))
+    indices = torch.zeros(n_query, n_pow2, device=dev, dtype=torch.int64)
+    args = [t.contiguous() for t in (data, part1, part2, cells, base_sims, is_empty, cell_start, cell_size, tot_size, n_probe_list)]
+    rc = fn(*[C.c_void_p(t.data_ptr()) for t in args], C.c_void_p(values.data_ptr()), C.c_void_p(indices.data_ptr()),
+            n_data, n_query, n_probe, n_pow2, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"reference kernel launch failed: cudaError {rc}")
+    return values[:, :k], indices[:, :k]

@@ -77,5 +77,35 @@ for name in ("c2", "c4"):
     out[f"{name}_search"] = {"nq": nq, "ms_per_batch": ms, "qps": nq / ms * 1e3, "recall_at_100": rec, "workload": wl[8]}
     print(out[f"{name}_search"], flush=True)
     del index, base
+if "c3sweep" in which or "build" in which:
+    wl = bench.WORKLOADS["c3"]
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    index, base = bench.build_index(wl, dev)
+    torch.cuda.synchronize(); t_build = time.perf_counter() - t0
+    out["c3_build"] = {"seconds_total": t_build, "what": "gen 10M x 128 randn + train (4+4 Lloyd iters on 1M) + encode 10M + container_add",
+                       "reference_T4_sift1m": "train 4.45 s + add 10.72 s for 1M (BASELINE.md)"}
+    # add path alone: encode + place 1M fresh vectors into an empty index with the trained codebooks
+    from torchpq_b200 import build
+    ix2 = T.IVFPQIndex(wl[1], wl[2], wl[3], initial_size=4096, device="cuda:0")
+    ix2.vq_codec.set_codebook(index.vq_codec.codebook); ix2.pq_codec.set_codebook(index.pq_codec.codebook)
+    xb = base[:, :1_000_000].contiguous()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ix2.add(xb)
+    torch.cuda.synchronize(); out["add_1M"] = {"seconds": time.perf_counter() - t0, "vectors_per_s": 1e6 / (time.perf_counter() - t0)}
+    print(out["c3_build"], out["add_1M"], flush=True)
+    del ix2, xb
+    if "c3sweep" in which:
+        k = wl[5]
+        res = {}
+        for nq in (1, 10, 100, 1000, 10000):
+            xs = [x.to(dev) for x in bench.gen_queries(wl[1], nq, 4, dev)]
+            i = [0]
+            def step():
+                index.search(xs[i[0] % 4], k=k); i[0] += 1
+            ms = timeit(step, reps=20)
+            res[nq] = {"ms_per_batch": ms, "qps": nq / ms * 1e3}
+        out["c3_batch_size_sweep"] = res
+        print(res, flush=True)
+    del index, base
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/aux_bench.json", "w"), indent=1)

@@ -43,8 +43,8 @@ def test_version_and_error_channel():
 
 def test_struct_layout_matches_header():
     import torchpq_b200 as T
-    # 4 int32 + int64 + 7 ptr + 4 int32 + int64 + 5 ptr
-    assert C.sizeof(T._lib.TpqIndex) == 16 + 8 + 7 * 8 + 16 + 8 + 5 * 8
+    # 4 int32 + int64 + 7 ptr + 4 int32 + int64 + 5 ptr + ptr + 2 int32
+    assert C.sizeof(T._lib.TpqIndex) == 16 + 8 + 7 * 8 + 16 + 8 + 5 * 8 + 8 + 8
 
 
 def test_no_cpu_path():

@@ -1,0 +1,62 @@
+"""Residual IVFPQ (pq_use_residual=True): ours == oracle == the reference's own
+`ivfpq_topk_residual_precomputed` kernel (oracle/_ref)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ivfpq_oracle as O, build_state as B, ref_kernels as R
+from helpers import assert_close_results
+
+pytestmark = pytest.mark.gpu
+
+
+def make_residual_index(st, device="cuda:0"):
+    import torchpq_b200 as T
+    ix = T.IVFPQIndex(st.d_vector, st.n_subvectors, st.n_cells, initial_size=1, device=device, pq_use_residual=True)
+    return ix.load_state(st)
+
+
+@pytest.mark.parametrize("M,d,smart", [(8, 32, True), (64, 128, False), (16, 64, True)])
+def test_residual_search_matches_oracle_and_reference_kernel(cuda_device, M, d, smart):
+    torch.manual_seed(M)
+    base = torch.randn(d, 5000)
+    st = B.build_state_residual(base, M, 16)
+    st.n_probe, st.use_smart_probing = 6, smart
+    x = torch.randn(d, 64)
+    k = 20
+    ov, oi, oa = O.search_residual(st, x, k=k + 1, return_address=True)
+    ix = make_residual_index(st)
+    v, i, a = ix.search(x.cuda(), k=k, return_address=True)
+    assert_close_results(v.cpu().numpy(), i.cpu().numpy(), ov[:, :k], oi[:, :k], rtol=1e-3, min_overlap=0.995)
+    if R.available(M):
+        xx, sims, cells, npl = O.coarse_probe(st, x)
+        p1, p2 = O.residual_parts(xx, torch.from_numpy(st.vq_codebook), torch.from_numpy(st.pq_codebook))
+        cn = cells.numpy()
+        g = lambda t: torch.as_tensor(t).cuda()
+        rv, ra = R.ivfpq_topk_residual_precomputed(g(st.storage), p1.cuda(), p2.cuda(), cells.cuda(), sims.cuda(),
+                                                   g(st.cell_start[cn]), g(st.cell_size[cn]), g(st.is_empty), npl.cuda(), k)
+        rv, ra = rv.cpu().numpy(), ra.cpu().numpy()
+        assert np.array_equal(rv, ov[:, :k])                       # oracle == reference kernel, bit for bit
+        tf = np.all(np.diff(ov, axis=1) != 0, axis=1)
+        assert np.array_equal(ra[tf], oa[tf, :k])
+        assert np.allclose(v.cpu().numpy(), rv, rtol=1e-3, atol=0)
+        assert (a.cpu().numpy()[tf] == ra[tf]).mean() >= 0.995
+
+
+def test_residual_train_add_search_and_decode(cuda_device):
+    import torchpq_b200 as T
+    import bench
+    torch.manual_seed(0)
+    base = torch.randn(32, 20000, device="cuda")
+    ix = T.IVFPQIndex(32, 16, 64, initial_size=64, device="cuda:0", pq_use_residual=True)
+    ix.train(base[:, :8000].contiguous())
+    ix.add(base)
+    ix.n_probe = 16
+    x = torch.randn(32, 100, device="cuda")
+    v, i = ix.search(x, k=10)
+    ov, oi = O.search_residual(bench.to_oracle_state(ix), x.cpu(), k=10)
+    assert_close_results(v.cpu().numpy(), i.cpu().numpy(), ov, oi, rtol=1e-3, min_overlap=0.995)
+    codes, cells = ix.encode(base[:, :100].contiguous())
+    rec = ix.decode((codes, cells))
+    err_res = (rec - base[:, :100]).norm() / base[:, :100].norm()
+    assert err_res < 0.6                                          # residual quantisation reconstructs the vectors

@@ -34,6 +34,7 @@ class TpqIndex(C.Structure):
         ("n_blocks", C.c_int64),
         ("codes_scan", C.c_void_p), ("block_valid", C.c_void_p), ("cell_block_start", C.c_void_p),
         ("pq_codebook_t", C.c_void_p), ("pq_norm_t", C.c_void_p),
+        ("part2_scan", C.c_void_p), ("residual", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -56,7 +57,9 @@ SIGNATURES = {
     "tpq_relayout_codebook": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "tpq_search_workspace_bytes": (_SZ, [_IX, _I, _I, _I]),
     "tpq_ivfpq_search": (_I, [_IX, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _SZ, _P]),
-    "tpq_ivfpq_search_cells": (_I, [_IX, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "tpq_ivfpq_search_cells": (_I, [_IX, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "tpq_part2_scan_bytes": (_SZ, [_I, _I]),
+    "tpq_relayout_part2": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "tpq_max_sim": (_I, [_P, _P, _I, _I, _I64, _I, _I, _I, _P, _P, _P]),
     "tpq_compute_centroids_workspace_bytes": (_SZ, [_I, _I]),
     "tpq_compute_centroids": (_I, [_P, _P, _I, _I, _I64, _I, _P, _P, _SZ, _P]),

@@ -55,6 +55,8 @@ def train(index, x: torch.Tensor, seed: int = 0, vq_iters: int = 15, pq_iters: i
     if index.distance == "cosine":
         x = fn.normalize(x.contiguous())
     vq = multi_kmeans(x[None].contiguous(), index.n_cells, vq_iters, seed=seed)[0].contiguous()
+    if getattr(index, "pq_use_residual", False):                       # IVFPQIndex.py:248-256: PQ learns x - vq(x)
+        x = x - vq[:, _assign(x[None].contiguous(), vq[None])[0]]
     sub = x.reshape(index.n_subvectors, index.d_subvector, x.shape[1]).contiguous()
     pq = multi_kmeans(sub, 256, pq_iters, seed=seed + 1).contiguous()
     index.vq_codec.set_codebook(vq)
@@ -65,7 +67,9 @@ def train(index, x: torch.Tensor, seed: int = 0, vq_iters: int = 15, pq_iters: i
 def encode(index, x: torch.Tensor):
     """-> (cells [n] i64, codes [M, n] u8) for x [d, n] (already normalised for cosine)."""
     cells = _assign(x[None], index.vq_codec.codebook[None])[0]
-    sub = x.reshape(index.n_subvectors, index.d_subvector, x.shape[1])
+    if getattr(index, "pq_use_residual", False):                       # IVFPQIndex.py:281-284
+        x = x - index.vq_codec.codebook[:, cells]
+    sub = x.reshape(index.n_subvectors, index.d_subvector, x.shape[1]).contiguous()
     codes = _assign(sub, index.pq_codec.codebook).to(torch.uint8)
     return cells, codes
 

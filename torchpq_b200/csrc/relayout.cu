@@ -114,9 +114,48 @@ __global__ void relayout_codebook_kernel(const float* __restrict__ cb, int M, in
   nrm[idx] = (metric == TPQ_METRIC_EUCLIDEAN) ? b2 : 0.f;
 }
 
+// part2_scan[c][g][code][s] = -2 * sum_i vq[(64g+s)*dsub + i][c] * pq[64g+s][i][code] - (||p||)^2, zero for padding
+// sub-quantizers.  ||p||^2 is formed as norm * norm, the way the reference's `.norm(dim=1).pow(2)` does (IVFPQIndex.py:167-170).
+__global__ void __launch_bounds__(256)
+relayout_part2_kernel(const float* __restrict__ vq, const float* __restrict__ pq, int M, int MP, int dsub, int C,
+                      float* __restrict__ out) {
+  const int c = blockIdx.x, code = threadIdx.x;
+  const int MG = (MP + 63) / 64;
+  float* o = out + (size_t)c * MG * 16384;
+  for (int m = 0; m < MG * 64; ++m) {
+    float y = 0.f;
+    if (m < M) {
+      float dot = 0.f, n2 = 0.f;
+      for (int i = 0; i < dsub; ++i) {
+        const float pv = pq[((size_t)m * dsub + i) * 256 + code];
+        dot = fmaf(vq[(size_t)(m * dsub + i) * C + c], pv, dot);
+        n2 = fmaf(pv, pv, n2);
+      }
+      const float nrm = sqrtf(n2);
+      y = __fsub_rn(__fmul_rn(dot, -2.f), __fmul_rn(nrm, nrm));
+    }
+    o[(size_t)(m >> 6) * 16384 + code * 64 + (m & 63)] = y;
+  }
+}
+
 }  // namespace tpq
 
 using namespace tpq;
+
+extern "C" size_t tpq_part2_scan_bytes(int M, int n_cells) {
+  const int MP = (M + 31) / 32 * 32;
+  return (size_t)n_cells * ((MP + 63) / 64) * 65536;
+}
+
+extern "C" int tpq_relayout_part2(const float* vq_codebook, const float* pq_codebook, int d, int M, int n_cells,
+                                  float* part2_scan, void* stream) {
+  TPQ_REQUIRE(vq_codebook && pq_codebook && part2_scan, "tpq_relayout_part2: null pointer");
+  TPQ_REQUIRE(d > 0 && M > 0 && d % M == 0 && n_cells > 0, "tpq_relayout_part2: bad sizes");
+  const int MP = (M + 31) / 32 * 32;
+  relayout_part2_kernel<<<n_cells, 256, 0, (cudaStream_t)stream>>>(vq_codebook, pq_codebook, M, MP, d / M, n_cells, part2_scan);
+  TPQ_LAUNCH_CHECK("relayout_part2_kernel");
+  return TPQ_OK;
+}
 
 extern "C" int tpq_relayout_plan(const int64_t* cell_size, int n_cells, int shard_rank, int shard_world,
                                  int32_t* cell_block_start, void* stream) {

@@ -146,6 +146,7 @@ struct Scanner {
   uint32_t regs[2][16];
   CtaTopK tk;
   uint64_t thr;
+  float base;                                           // residual IVFPQ: coarse similarity of the current cell (else 0)
   int seg, seg_lo, seg_hi, seg_b0; uint32_t seg_a0;     // current probe segment, cached in registers
   int64_t B_cur, B_nxt; uint32_t a0_cur, a0_nxt, valid_cur, valid_nxt;
 
@@ -174,7 +175,7 @@ struct Scanner {
   __device__ __forceinline__ void process_block(bool has_next) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     step<PAR, 0>(acc, has_next);
-    const float score = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    const float score = base + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
     const uint64_t key = make_key(score, a0_cur + lane);
     const bool live = (valid_cur >> lane) & 1u;
     if (PAR == 0) thr = tk.threshold();                  // running k-th best of the CTA
@@ -194,7 +195,7 @@ struct Scanner {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     simple_units<0>(acc, B);
     const uint32_t v = __ldg(valid + B);
-    const float score = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    const float score = base + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
     return ((v >> lane) & 1u) ? make_key(score, a0 + lane) : 0ull;
   }
   __device__ __forceinline__ void run(int b, int b_end) {
@@ -219,10 +220,12 @@ struct Scanner {
   }
 };
 
-struct ScanSmem { size_t lut, seg_blk0, seg_addr0, seg_prefix, thr, lock, list, bufs, total; };
-static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp) {
+struct ScanSmem { size_t lut, part1, seg_blk0, seg_addr0, seg_cell, seg_prefix, thr, lock, list, bufs, total; };
+static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp, bool residual = false) {
   ScanSmem s; size_t off = 0;
   s.lut = off;        off += (size_t)((MP + 63) / 64) * 65536;
+  s.part1 = off;      off += residual ? (size_t)((MP + 63) / 64) * 65536 : 0;   // query half of the residual LUT
+  s.seg_cell = off;   off += residual ? (size_t)n_probe * 4 : 0;
   s.seg_blk0 = off;   off += (size_t)n_probe * 4;
   s.seg_addr0 = off;  off += (size_t)n_probe * 4;
   s.seg_prefix = off; off += (size_t)(n_probe + 1) * 4;
@@ -240,6 +243,8 @@ struct ScanArgs {
   const float* lut_scan;          // [nq_chunk][MG][256][64] (staged-LUT variant, DSUB == 0)
   const float* x;                 // [d, nq] queries (in-CTA LUT variant)
   const float* cbt;               // pq_codebook_t [256, MP, dsub]
+  const float* part2_scan;        // residual: [C][MG][256][64] per-cell half of the LUT
+  const float* base_sims;         // residual: [nq, n_probe] coarse similarities
   int M, metric;
   const int64_t* cells;           // [nq, n_probe]
   const int64_t* n_probe_list;    // [nq]
@@ -249,7 +254,11 @@ struct ScanArgs {
 
 // DSUB > 0: the CTA builds its query's LUT itself from the (L2-resident) transposed codebook -- no LUT
 // round trip through HBM, no LUT workspace.  DSUB == 0: the LUT was written by lut_scan_kernel and is copied in.
-template <int MP, int NW, int MINB, int DSUB>
+// RES: residual IVFPQ (ivfpq_topk_residual_precomputed, ivfpq_topk.cu:1039-1207).  The LUT of a (query, cell) pair
+// is part1[query] + part2[cell]: the query half is built once into a second shared-memory table, and the CTA
+// walks the probed cells in lock step, re-forming the LUT (one float4 add per 16 bytes) before each cell; the
+// cell's coarse similarity seeds every score.
+template <int MP, int NW, int MINB, int DSUB, bool RES>
 __global__ void __launch_bounds__(NW * 32, MINB)
 ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -265,7 +274,9 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
 
   // --- probe segments first (warp 0): their dependent global loads overlap the other warps' LUT work (same visiting rules as scan_ref.cu / ivfpq_topk.cu:837-870)
   int P = (int)A.n_probe_list[q];
-  P = max(1, min(P, A.n_probe));
+  P = RES ? max(0, min(P, A.n_probe))                         // residual kernel: `for cCell < nProbe` (:1080), may be empty
+          : max(1, min(P, A.n_probe));                        // plain kernel: first cell entered unconditionally
+  int32_t* seg_cell = reinterpret_cast<int32_t*>(smem + L.seg_cell);
   if (warp == 0) {
     int carry = 0;
     if (lane == 0) seg_prefix[0] = 0;
@@ -281,6 +292,7 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
         nb = skip ? 0 : A.cell_block_start[c + 1] - b0;
         seg_blk0[j] = b0;
         seg_addr0[j] = (uint32_t)s;
+        if constexpr (RES) seg_cell[j] = (int32_t)c;
       }
       int incl = nb;
       #pragma unroll
@@ -313,7 +325,7 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       }
       a2[h] = s2;
     }
-    float* lutf = reinterpret_cast<float*>(lut);
+    float* lutf = reinterpret_cast<float*>(RES ? smem + L.part1 : lut);
     #pragma unroll 8
     for (int c = warp; c < 256; c += NW) {
       #pragma unroll
@@ -327,7 +339,8 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
         #pragma unroll
         for (int i = 0; i < DSUB; ++i) { dot = fmaf(xr[h][i], pv[i], dot); b2 = __fadd_rn(b2, __fmul_rn(pv[i], pv[i])); }
         float y = dot;
-        if (A.metric == TPQ_METRIC_EUCLIDEAN) y = __fsub_rn(__fsub_rn(__fmul_rn(dot, 2.f), a2[h]), b2);
+        if constexpr (RES) y = __fmul_rn(dot, 2.f);                    // part1 = 2 <x_m, p> (IVFPQIndex.py:377)
+        else if (A.metric == TPQ_METRIC_EUCLIDEAN) y = __fsub_rn(__fsub_rn(__fmul_rn(dot, 2.f), a2[h]), b2);
         lutf[(h >> 1) * 16384 + c * 64 + (h & 1) * 32 + lane] = y;
       }
     }
@@ -351,10 +364,32 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   const int total = seg_prefix[P];
   const int b_begin = (int)(((int64_t)total * slice) / A.S);
   const int b_end = (int)(((int64_t)total * (slice + 1)) / A.S);
-  sc.thr = 0;
+  sc.thr = 0; sc.base = 0.f;
   sc.seg = 0; sc.seg_lo = 0; sc.seg_hi = seg_prefix[1]; sc.seg_b0 = seg_blk0[0]; sc.seg_a0 = seg_addr0[0];
   CtaTopK& tk = sc.tk;
   uint64_t* bufs = reinterpret_cast<uint64_t*>(smem + L.bufs);
+  if constexpr (RES) {
+    const float4* p1 = reinterpret_cast<const float4*>(smem + L.part1);
+    float4* dst = reinterpret_cast<float4*>(lut);
+    for (int j = 0; j < P; ++j) {
+      const int b0 = seg_prefix[j], b1 = seg_prefix[j + 1];
+      if (b1 == b0) continue;                                          // skipped entry, empty cell or another shard's cell
+      __syncthreads();                                                 // every warp is done with the previous cell's LUT
+      const float4* p2 = reinterpret_cast<const float4*>(A.part2_scan + (size_t)seg_cell[j] * MG * 16384);
+      #pragma unroll 4
+      for (int i = tid; i < MG * 4096; i += NW * 32) {                 // store_precomputed_to_smem: part1 + part2 (:609-628)
+        const float4 a = p1[i], b = __ldg(p2 + i);
+        dst[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      }
+      __syncthreads();
+      sc.base = A.base_sims[(size_t)q * A.n_probe + j];
+      sc.run(b0 + warp, b1);
+    }
+    tk.cta_flush(bufs, NW, lane, warp);
+    uint64_t* outr = A.keys_out + (size_t)q * A.k;
+    for (int i = tid; i < A.k; i += NW * 32) outr[i] = tk.list[i];
+    return;
+  }
   // bootstrap: the first two blocks of every warp go to the list unfiltered through ONE CTA-wide sort, which
   // establishes the threshold (k-th best of the first NW * 64 vectors) without 2 * NW lock-serialised flushes
   {
@@ -431,9 +466,10 @@ static int g_prof_n = 0;
 static cudaEvent_t g_prof_start[kProfMax], g_prof_stop[kProfMax];
 static bool g_prof_created = false;
 
-static int pick_slices(int nq, int k) {
+static int pick_slices(const tpq_index* ix, int nq, int k) {
   // enough CTAs for ~2 waves of 2 CTAs/SM when the batch is small
   (void)k;
+  if (ix->residual) return 1;                                 // the residual kernel walks whole probe lists
   const int want = 148 * 4;
   if (nq >= want) return 1;
   int s = (want + nq - 1) / nq;
@@ -456,7 +492,7 @@ static SearchWs search_ws(const tpq_index* ix, int nq, int n_probe, int k) {
   SearchWs w; size_t off = 0;
   const int MG = (ix->m_pad + 63) / 64;
   const int chunk = nq < kQueryChunk ? nq : kQueryChunk;
-  const int S = pick_slices(nq, k);
+  const int S = pick_slices(ix, nq, k);
   w.coarse = off;     off += align_up(tpq_coarse_workspace_bytes(ix->d_vector, nq, ix->n_cells), 256);
   w.probe_sims = off; off += align_up((size_t)nq * n_probe * 4, 256);
   w.cells = off;      off += align_up((size_t)nq * n_probe * 8, 256);
@@ -468,16 +504,17 @@ static SearchWs search_ws(const tpq_index* ix, int nq, int n_probe, int k) {
   return w;
 }
 
-template <int MP, int NW, int MINB, int DSUB>
+template <int MP, int NW, int MINB, int DSUB, bool RES = false>
 static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cells, const int64_t* npl,
-                         int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st) {
+                         int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st,
+                         const float* base_sims = nullptr) {
   const int kp = next_pow2(k < 32 ? 32 : k);
-  ScanSmem L = scan_smem(MP, n_probe, NW, kp);
+  ScanSmem L = scan_smem(MP, n_probe, NW, kp, RES);
   if (L.total > 227 * 1024) {
     set_error("scan: M=%d n_probe=%d k=%d needs %zu B of shared memory (> 227 KB)", ix->n_subvectors, n_probe, k, L.total);
     return TPQ_ERR_UNSUPPORTED;
   }
-  auto kern = ivfpq_scan_kernel<MP, NW, MINB, DSUB>;
+  auto kern = ivfpq_scan_kernel<MP, NW, MINB, DSUB, RES>;
   TPQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   const int MG = (MP + 63) / 64;
   const int dsub = ix->d_vector / ix->n_subvectors;
@@ -492,6 +529,7 @@ static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cel
     }
     ScanArgs A;
     A.x = x; A.cbt = ix->pq_codebook_t; A.M = ix->n_subvectors; A.metric = ix->metric;
+    A.part2_scan = ix->part2_scan; A.base_sims = base_sims;
     A.codes = ix->codes_scan; A.valid = ix->block_valid; A.cell_block_start = ix->cell_block_start;
     A.cell_start = ix->cell_start; A.lut_scan = lut_ws; A.cells = cells; A.n_probe_list = npl; A.keys_out = keys;
     A.nq = nq; A.q_base = q0; A.n_probe = n_probe; A.k = k; A.kp = kp; A.S = S;
@@ -533,7 +571,22 @@ static int check_index(const tpq_index* ix) {
 }
 
 static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cells, const int64_t* npl,
-                         int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st) {
+                         int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st,
+                         const float* base_sims = nullptr) {
+  if (ix->residual) {
+    // residual IVFPQ: two 64 KB tables per CTA -> one 16-warp CTA per SM; M <= 64 and d/M in {1,2,4} for now
+    const int dsub = ix->d_vector / ix->n_subvectors;
+    if (!ix->part2_scan || !base_sims) { set_error("residual search needs part2_scan and base_sims"); return TPQ_ERR_BAD_ARG; }
+    if (ix->metric != TPQ_METRIC_EUCLIDEAN) { set_error("residual IVFPQ is defined for the euclidean metric"); return TPQ_ERR_UNSUPPORTED; }
+    if (ix->m_pad > 64 || !(dsub == 1 || dsub == 2 || dsub == 4)) {
+      set_error("residual IVFPQ: n_subvectors=%d, d_subvector=%d not supported yet (need M <= 64, d/M in {1,2,4})", ix->n_subvectors, dsub);
+      return TPQ_ERR_UNSUPPORTED;
+    }
+#define TPQ_RES(MPv, DS) launch_scan_d<MPv, 16, 1, DS, true>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, base_sims)
+    if (ix->m_pad == 32) return dsub == 1 ? TPQ_RES(32, 1) : dsub == 2 ? TPQ_RES(32, 2) : TPQ_RES(32, 4);
+    return dsub == 1 ? TPQ_RES(64, 1) : dsub == 2 ? TPQ_RES(64, 2) : TPQ_RES(64, 4);
+#undef TPQ_RES
+  }
 #define TPQ_SCAN_ARGS ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st
   // tuning knob for experiments (scripts/sweep_scan.py): TPQ_SCAN_CFG = "<warps>x<min CTAs/SM>"
   const char* cfg = getenv("TPQ_SCAN_CFG");
@@ -595,7 +648,7 @@ extern "C" size_t tpq_search_workspace_bytes(const tpq_index* ix, int nq, int n_
   return search_ws(ix, nq, n_probe, k).total;
 }
 
-extern "C" int tpq_ivfpq_search_cells(const tpq_index* ix, const float* x_dn, const int64_t* cells,
+extern "C" int tpq_ivfpq_search_cells(const tpq_index* ix, const float* x_dn, const int64_t* cells, const float* base_sims,
                                       const int64_t* n_probe_list, int nq, int n_probe, int k,
                                       float* values, int64_t* ids, int64_t* address, uint64_t* keys_out,
                                       void* ws, size_t ws_bytes, void* stream) {
@@ -608,10 +661,10 @@ extern "C" int tpq_ivfpq_search_cells(const tpq_index* ix, const float* x_dn, co
   if (!ws || ws_bytes < W.total) { set_error("workspace too small (%zu < %zu)", ws_bytes, W.total); return TPQ_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* w = reinterpret_cast<uint8_t*>(ws);
-  const int S = pick_slices(nq, k);
+  const int S = pick_slices(ix, nq, k);
   uint64_t* keys = reinterpret_cast<uint64_t*>(w + W.keys);
   if (int rc = scan_dispatch(ix, x_dn, cells, n_probe_list, nq, n_probe, k, S,
-                             reinterpret_cast<float*>(w + W.lut), keys, st)) return rc;
+                             reinterpret_cast<float*>(w + W.lut), keys, st, base_sims)) return rc;
   return launch_merge(keys, nq, S, k, k, (int64_t)S * k, ix->address2id, ix->capacity, values, ids, address, keys_out, st);
 }
 
@@ -639,9 +692,9 @@ extern "C" int tpq_ivfpq_search(const tpq_index* ix, const float* x_dn, int nq, 
   if (int rc = tpq_coarse_probe(x, ix->vq_codebook, ix->d_vector, nq, ix->n_cells, n_probe, smart, temperature,
                                 probe_sims, cells, npl, w + W.coarse, W.probe_sims - W.coarse, stream)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const int S = pick_slices(nq, k);
+  const int S = pick_slices(ix, nq, k);
   uint64_t* keys = reinterpret_cast<uint64_t*>(w + W.keys);
-  if (int rc = scan_dispatch(ix, x, cells, npl, nq, n_probe, k, S, reinterpret_cast<float*>(w + W.lut), keys, st)) return rc;
+  if (int rc = scan_dispatch(ix, x, cells, npl, nq, n_probe, k, S, reinterpret_cast<float*>(w + W.lut), keys, st, probe_sims)) return rc;
   return launch_merge(keys, nq, S, k, k, (int64_t)S * k, ix->address2id, ix->capacity, values, ids, address, keys_out, st);
 }
 

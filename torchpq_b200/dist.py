@@ -46,15 +46,17 @@ def sharded_search(index, x: torch.Tensor, k: int, group=None, return_address: b
         per = (nq + world - 1) // world
         lo = min(nq, rank * per)
         hi = min(nq, lo + per)
-        mine = torch.zeros(per, n_probe + 1, dtype=torch.long, device=x.device)
+        mine = torch.zeros(per, 2 * n_probe + 1, dtype=torch.long, device=x.device)
         if hi > lo:
-            _, cells, npl = fn.coarse_probe(xq[:, lo:hi].contiguous(), index.vq_codec.codebook, n_probe,
-                                            index.use_smart_probing, index.smart_probing_temperature)
+            sims, cells, npl = fn.coarse_probe(xq[:, lo:hi].contiguous(), index.vq_codec.codebook, n_probe,
+                                               index.use_smart_probing, index.smart_probing_temperature)
             mine[:hi - lo, :n_probe] = cells
             mine[:hi - lo, n_probe] = npl
+            mine[:hi - lo, n_probe + 1:] = sims.view(torch.int32).to(torch.long)      # fp32 bits, exact round trip
         allp = _gather_rows(mine, world, group)[:nq]
-        keys = index.search_cells(xq, allp[:, :n_probe].contiguous(), n_probe_list=allp[:, n_probe].contiguous(),
-                                  k=k, return_keys=True)[2]
+        base = allp[:, n_probe + 1:].to(torch.int32).view(torch.float32).contiguous()
+        keys = index.search_cells(xq, allp[:, :n_probe].contiguous(), base_sims=base,
+                                  n_probe_list=allp[:, n_probe].contiguous(), k=k, return_keys=True)[2]
     else:
         _, _, keys = index.search(x, k=k, return_keys=True)
     if world == 1:

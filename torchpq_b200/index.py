@@ -67,6 +67,14 @@ class ScanLayout:
         ix.cell_block_start = self.cell_block_start.data_ptr()
         ix.pq_codebook_t = self.pq_codebook_t.data_ptr()
         ix.pq_norm_t = self.pq_norm_t.data_ptr()
+        self.part2_scan = None
+        if getattr(index, "pq_use_residual", False):
+            # IVFPQIndex.precompute_part2 (IVFPQIndex.py:160-170), laid out like the shared-memory LUT
+            self.part2_scan = torch.empty(lib.tpq_part2_scan_bytes(M, Cn) // 4, dtype=torch.float32, device=dev)
+            check(lib.tpq_relayout_part2(ptr(index.vq_codec.codebook), ptr(index.pq_codec.codebook), d, M, Cn,
+                                         ptr(self.part2_scan), stream))
+            ix.part2_scan = self.part2_scan.data_ptr()
+            ix.residual = 1
         self.cindex = ix
         check(lib.tpq_relayout_codes(C.byref(ix), ptr(self.codes_scan), ptr(self.block_valid), stream))
         check(lib.tpq_relayout_codebook(ptr(index.pq_codec.codebook), d, M, ix.metric,
@@ -84,7 +92,11 @@ class IVFPQIndex(StateModule):
         assert distance in ("euclidean", "cosine"), \
             "the reference can only build/search euclidean and cosine IVFPQ indexes (MultiKMeans.py:82-115,218-223)"
         if pq_use_residual:
-            raise NotImplementedError("pq_use_residual=True (residual IVFPQ) is outside the ported hot path")
+            assert distance == "euclidean", "residual IVFPQ is defined on euclidean residuals"
+            # IVFPQIndex.py:52-55: the per-cell table is precomputed when it fits 4 GB; the on-the-fly variant
+            # (precomputed_adc_residual, IVFPQIndex.py:382-405) is not built here
+            if n_cells * 256 * n_subvectors * 4 > 4 * 1024 ** 3:
+                raise NotImplementedError("residual IVFPQ without the precomputed part-2 table is not supported")
         if initial_size is None:
             initial_size = expand_step_size                              # CellContainer.py:23-24
         assert initial_size >= 0 and n_cells > 0
@@ -92,7 +104,8 @@ class IVFPQIndex(StateModule):
         self.n_cells, self.code_size, self.contiguous_size = n_cells, n_subvectors, 4
         self.distance, self.device, self.verbose = distance, device, verbose
         self.initial_size, self.expand_step_size, self.expand_mode = initial_size, expand_step_size, expand_mode
-        self.pq_use_residual = False
+        self.pq_use_residual = bool(pq_use_residual)
+        self._use_precomputed = bool(pq_use_residual)
         self.n_probe = 1                                                 # IVFPQIndex.py:51
         self.use_smart_probing = True                                    # IVFPQIndex.py:58
         self.smart_probing_temperature = 30.0                            # IVFPQIndex.py:59
@@ -221,7 +234,12 @@ class IVFPQIndex(StateModule):
         keys = torch.empty(nq, k, dtype=torch.int64, device=dev) if return_keys else None
         ws_bytes = lib.tpq_search_workspace_bytes(C.byref(lay.cindex), nq, n_probe, k)
         ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
-        check(lib.tpq_ivfpq_search_cells(C.byref(lay.cindex), ptr(x), ptr(cells), ptr(n_probe_list), nq, n_probe, k,
+        if self.pq_use_residual:
+            assert base_sims is not None, "base_sims is required when pq_use_residual is True"   # IVFPQIndex.py:424
+            assert base_sims.shape == (nq, n_probe) and base_sims.dtype == torch.float32
+            base_sims = base_sims.contiguous()
+        check(lib.tpq_ivfpq_search_cells(C.byref(lay.cindex), ptr(x), ptr(cells),
+                                         ptr(base_sims if self.pq_use_residual else None), ptr(n_probe_list), nq, n_probe, k,
                                          ptr(values), ptr(ids), ptr(address), ptr(keys), ptr(ws), ws_bytes,
                                          _lib.current_stream(dev)))
         out = (values, ids)
@@ -286,18 +304,28 @@ class IVFPQIndex(StateModule):
         self._state_changed()
 
     def encode(self, x):
-        """IVFPQIndex.encode (IVFPQIndex.py:262-287): x [d_vector, n] -> PQ codes [n_subvectors, n] uint8."""
+        """IVFPQIndex.encode (IVFPQIndex.py:262-287): x [d_vector, n] -> PQ codes [n_subvectors, n] uint8
+        (residual index: (pq_code of x - vq centroid, vq_code), IVFPQIndex.py:281-284)."""
         assert len(x.shape) == 2 and x.shape[0] == self.d_vector
         from . import build, fn
         if self.distance == "cosine":
             x = fn.normalize(x.contiguous())
+        if self.pq_use_residual:
+            cells, codes = build.encode(self, x.contiguous())
+            return codes, cells
         sub = x.reshape(self.n_subvectors, self.d_subvector, x.shape[1])
         return build._assign(sub, self.pq_codec.codebook).to(torch.uint8)
 
     def decode(self, code):
-        """IVFPQIndex.decode (IVFPQIndex.py:289-314) -> PQCodec.decode (PQCodec.py:113-130): [M, n] u8 -> [d, n] f32."""
-        assert len(code.shape) == 2 and code.shape[0] == self.n_subvectors
+        """IVFPQIndex.decode (IVFPQIndex.py:289-314) -> PQCodec.decode (PQCodec.py:113-130): [M, n] u8 -> [d, n] f32
+        (residual index: x = (pq_code, vq_code) -> vq centroid + decoded residual)."""
         from . import fn
+        if self.pq_use_residual:
+            assert len(code) == 2
+            pq_code, vq_code = code
+            assert pq_code.shape[0] == self.n_subvectors and pq_code.shape[1] == vq_code.shape[0]
+            return self.vq_codec.codebook[:, vq_code] + fn.pq_decode(self.pq_codec.codebook, pq_code)
+        assert len(code.shape) == 2 and code.shape[0] == self.n_subvectors
         return fn.pq_decode(self.pq_codec.codebook, code)
 
     def get_id_by_address(self, address):
