@@ -20,7 +20,10 @@ lib = T._lib.lib
 for smart in (True,):
     index.use_smart_probing = smart
     for cfg in cfgs:
-        os.environ["TPQ_SCAN_CFG"] = cfg
+        if cfg.startswith("boot"):
+            os.environ["TPQ_BOOT_R"] = cfg[4:]; os.environ.pop("TPQ_SCAN_CFG", None)
+        else:
+            os.environ["TPQ_SCAN_CFG"] = cfg
         for i in range(2):
             index.search(xs[i], k=k)
         torch.cuda.synchronize()

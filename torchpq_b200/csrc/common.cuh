@@ -199,17 +199,38 @@ struct CtaTopK {
     if (cnt > kTopkBuf - 32) flush(lane);
   }
   // Whole-CTA flush (every thread calls it): the staging buffers of all warps (`bufs`, nw * kTopkBuf entries,
-  // contiguous, a power of two in total) are sorted together by the CTA and merged into the list once, instead of
-  // nw lock-serialised warp flushes.  Used to bootstrap the threshold and to drain the buffers at the end.
-  __device__ __forceinline__ void cta_flush(uint64_t* bufs, int nw, int lane, int warp) {
-    for (int i = cnt + lane; i < kTopkBuf; i += 32) buf[i] = 0;   // pad this warp's unused slots
+  // contiguous) are compacted, sorted together by the CTA and merged into the list once, instead of nw
+  // lock-serialised warp flushes.  Used to bootstrap the threshold and to drain the buffers at the end.  Only the
+  // smallest power of two that holds the live entries is sorted.  `scratch` is an int[nw + 1] in shared memory.
+  __device__ __forceinline__ void cta_flush(uint64_t* bufs, int* scratch, int nw, int lane, int warp) {
+    // compaction: every thread picks its (up to two) entries up into registers, then writes them at the warp's offset
+    const uint64_t e0 = lane < cnt ? buf[lane] : 0ull;
+    const uint64_t e1 = lane + 32 < cnt ? buf[lane + 32] : 0ull;
+    if (lane == 0) scratch[warp + 1] = cnt;
+    if (threadIdx.x == 0) scratch[0] = 0;
     __syncthreads();
-    const int nb = nw * kTopkBuf;
-    cta_sort_desc(bufs, nb);
-    if (warp == 0) {
-      const int take = nb < kp ? nb : kp;
-      warp_merge_desc(list, kp, bufs, take, lane);
-      if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(thr) = list[k - 1];
+    if (warp == 0) {                                                 // inclusive scan of the nw counts (nw <= 32)
+      int v = lane < nw ? scratch[lane + 1] : 0;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+      if (lane < nw) scratch[lane + 1] = v;
+    }
+    __syncthreads();
+    const int total = scratch[nw], off0 = scratch[warp];
+    int nb = 32;
+    while (nb < total) nb <<= 1;                                     // <= nw * kTopkBuf by construction
+    if (lane < cnt) bufs[off0 + lane] = e0;
+    if (lane + 32 < cnt) bufs[off0 + lane + 32] = e1;
+    __syncthreads();
+    for (int i = total + threadIdx.x; i < nb; i += blockDim.x) bufs[i] = 0;
+    __syncthreads();
+    if (total > 0) {                                                 // CTA-uniform
+      cta_sort_desc(bufs, nb);
+      if (warp == 0) {
+        const int take = nb < kp ? nb : kp;
+        warp_merge_desc(list, kp, bufs, take, lane);
+        if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(thr) = list[k - 1];
+      }
     }
     cnt = 0;
     __syncthreads();

@@ -220,7 +220,7 @@ struct Scanner {
   }
 };
 
-struct ScanSmem { size_t lut, part1, seg_blk0, seg_addr0, seg_cell, seg_prefix, thr, lock, list, bufs, total; };
+struct ScanSmem { size_t lut, part1, seg_blk0, seg_addr0, seg_cell, seg_prefix, thr, lock, scratch, list, bufs, total; };
 static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp, bool residual = false) {
   ScanSmem s; size_t off = 0;
   s.lut = off;        off += (size_t)((MP + 63) / 64) * 65536;
@@ -232,6 +232,7 @@ static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp, bool residual = f
   off = align_up(off, 8);
   s.thr = off;        off += 8;
   s.lock = off;       off += 8;
+  s.scratch = off;    off += align_up((size_t)(nw + 1) * 4, 8);
   s.list = off;       off += (size_t)kp * 8;
   s.bufs = off;       off += (size_t)nw * kTopkBuf * 8;
   s.total = off;
@@ -250,6 +251,7 @@ struct ScanArgs {
   const int64_t* n_probe_list;    // [nq]
   uint64_t* keys_out;             // [nq, S, k]
   int nq, q_base, n_probe, k, kp, S;
+  int boot_r;                     // blocks per warp in the bootstrap (1 or 2)
 };
 
 // DSUB > 0: the CTA builds its query's LUT itself from the (L2-resident) transposed codebook -- no LUT
@@ -368,6 +370,7 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   sc.seg = 0; sc.seg_lo = 0; sc.seg_hi = seg_prefix[1]; sc.seg_b0 = seg_blk0[0]; sc.seg_a0 = seg_addr0[0];
   CtaTopK& tk = sc.tk;
   uint64_t* bufs = reinterpret_cast<uint64_t*>(smem + L.bufs);
+  int* scratch = reinterpret_cast<int*>(smem + L.scratch);
   if constexpr (RES) {
     const float4* p1 = reinterpret_cast<const float4*>(smem + L.part1);
     float4* dst = reinterpret_cast<float4*>(lut);
@@ -385,24 +388,26 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       sc.base = A.base_sims[(size_t)q * A.n_probe + j];
       sc.run(b0 + warp, b1);
     }
-    tk.cta_flush(bufs, NW, lane, warp);
+    tk.cta_flush(bufs, scratch, NW, lane, warp);
     uint64_t* outr = A.keys_out + (size_t)q * A.k;
     for (int i = tid; i < A.k; i += NW * 32) outr[i] = tk.list[i];
     return;
   }
-  // bootstrap: the first two blocks of every warp go to the list unfiltered through ONE CTA-wide sort, which
-  // establishes the threshold (k-th best of the first NW * 64 vectors) without 2 * NW lock-serialised flushes
+  // bootstrap: the first R blocks of every warp go to the list unfiltered through ONE CTA-wide sort, which
+  // establishes the threshold (k-th best of the first R * NW * 32 vectors) without R * NW lock-serialised flushes.
+  // R = 1 when that already yields k candidates (k <= 32 NW), else 2 (the staging buffers hold two blocks).
+  const int R = A.boot_r;
   {
     #pragma unroll 1
-    for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < R; ++r) {
       const int b = b_begin + warp + r * NW;
       tk.buf[r * 32 + lane] = (b < b_end) ? sc.key_of_block(b) : 0ull;
     }
-    tk.cnt = kTopkBuf;
-    tk.cta_flush(bufs, NW, lane, warp);
+    tk.cnt = R * 32;
+    tk.cta_flush(bufs, scratch, NW, lane, warp);
   }
-  sc.run(b_begin + warp + 2 * NW, b_end);
-  tk.cta_flush(bufs, NW, lane, warp);                          // drain every warp's staging buffer with one CTA-wide sort
+  sc.run(b_begin + warp + R * NW, b_end);
+  tk.cta_flush(bufs, scratch, NW, lane, warp);                 // drain every warp's staging buffer with one CTA-wide sort
   uint64_t* out = A.keys_out + ((size_t)q * A.S + slice) * A.k;
   for (int i = tid; i < A.k; i += NW * 32) out[i] = tk.list[i];
 }
@@ -533,6 +538,7 @@ static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cel
     A.codes = ix->codes_scan; A.valid = ix->block_valid; A.cell_block_start = ix->cell_block_start;
     A.cell_start = ix->cell_start; A.lut_scan = lut_ws; A.cells = cells; A.n_probe_list = npl; A.keys_out = keys;
     A.nq = nq; A.q_base = q0; A.n_probe = n_probe; A.k = k; A.kp = kp; A.S = S;
+    { const char* br = getenv("TPQ_BOOT_R"); A.boot_r = br ? atoi(br) : 2; if (A.boot_r < 1 || A.boot_r > 2) A.boot_r = 2; }
     const bool prof = g_prof_on && g_prof_n < kProfMax;
     if (prof) cudaEventRecord(g_prof_start[g_prof_n], st);
     kern<<<n * S, NW * 32, L.total, st>>>(A, L);
