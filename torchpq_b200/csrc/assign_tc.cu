@@ -19,10 +19,10 @@
 // over the TMEM accumulator (4 lane quadrants x 2 column halves), warps 10..17 = finishers (exact similarity + stores),
 // two groups alternating tiles so the dependent fp32 chain of one tile overlaps the next tile's arg-max.
 //
-// Bound (measured, profiles/r01_assign_tc_raw.csv): the arg-max must read every accumulator back, n*k*4 bytes of
-// TMEM reads (C5: 65 GB) against ~64 B/clk/SM of tcgen05.ld bandwidth = ~3.6 ms; the HBM stream (17.2 GB) would
-// take 2.65 ms.  Round 1 reaches 5.6 ms (3.0 TB/s of HBM traffic, tensor pipe 38 % busy).  Three pipelines: A stages (TMA -> MMA + epilogue), the
-// resident B tile (reloaded when the CTA's tile range crosses into the next k-means), two TMEM accumulators.
+// Measured (profiles/r01_assign_tc_raw.csv, C5): 5.6 ms = 3.0 TB/s of HBM traffic (the stream alone would take
+// 2.65 ms), tensor pipe 38 % busy, issue slots 63 % busy, L1/shared pipe 57 % busy of which two thirds are bank
+// conflicts of the finishers' centroid-column gathers (random columns of the swizzled B tile) -- the next thing to
+// attack (TMEM read-back is only 4 % of its peak, so the arg-max read of the accumulators is not the limit).
 #include <cuda.h>
 #include "common.cuh"
 
