@@ -153,9 +153,10 @@ int tpq_ivfpq_search_cells(const tpq_index* index, const float* x_dn, const int6
  *   data [l, d, n], labels [l, n] i64 -> centroids [l, d, k] = member mean, 0 for an empty cluster.
  * tpq_pq_decode: PQDecodeCuda (kernels/PQDecodeCuda.py:38-65, kernels/cuda/pq_decode.cu:7-53):
  *   codebook [M, dsub, 256], code [M, n] u8 -> out [M*dsub, n] f32. */
-/* exact != 0: fp32 SIMT kernel, the reference's arithmetic bit for bit.  exact == 0: TF32 tcgen05 kernel where the
- * shape allows (euclidean, d % 8 == 0, d <= 64, k <= 256, n % 4 == 0): labels may differ from the exact ones only
- * between centroids closer than TF32 rounding; maxsims is still the exact fp32 value of the chosen centroid. */
+/* exact == 1: fp32 SIMT kernel, the reference's arithmetic bit for bit.  exact == 0 or 2: TF32 tcgen05 kernel where
+ * the shape allows (euclidean, d % 8 == 0, d <= 64, k <= 256, n % 4 == 0), else the exact kernel: labels may differ
+ * from the exact ones only between centroids closer than TF32 rounding.  maxsims: exact == 2 -> recomputed exactly
+ * in fp32 for the chosen centroid; exact == 0 -> 2*score - |x|^2 from the TF32 score (~1e-3 relative). */
 int tpq_max_sim(const float* data, const float* centroids, int l, int d, int64_t n, int k, int metric,
                 int exact, float* maxsims, int64_t* labels, void* stream);
 size_t tpq_compute_centroids_workspace_bytes(int l, int k);

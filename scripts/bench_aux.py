@@ -32,11 +32,12 @@ if "c5" in which or "centroids" in which:
     cent = data[:, :, :k].contiguous()
     if "c5" in which:
         byts = 4 * l * d * n + 4 * l * d * k + 12 * l * n
-        for exact, name, kern in ((False, "c5_max_sim_tc", "assign_tc_kernel (tcgen05 TF32 + exact fp32 maxsim)"),
-                                  (True, "c5_max_sim_exact", "max_sim_kernel (fp32 SIMT, exact)")):
+        for exact, ev, name, kern in ((False, False, "c5_max_sim_tc", "assign_tc_kernel (tcgen05 TF32, TF32-derived maxsim)"),
+                                      (False, True, "c5_max_sim_tc_exact_values", "assign_tc_kernel (tcgen05 TF32 + exact fp32 maxsim)"),
+                                      (True, True, "c5_max_sim_exact", "max_sim_kernel (fp32 SIMT, exact)")):
             if exact and "c5fast" in which:
                 continue
-            ms = timeit(lambda: T.fn.max_sim(data, cent, exact=exact), reps=3, warm=1)
+            ms = timeit(lambda: T.fn.max_sim(data, cent, exact=exact, exact_values=ev), reps=3, warm=1)
             out[name] = {"ms": ms, "algorithmic_GB": byts / 1e9, "GBps": byts / ms / 1e6, "frac_of_hbm_peak": byts / ms / 1e6 / peak,
                          "tflops_gemm_form": 2.0 * l * n * d * k / ms / 1e9, "kernel": kern}
             print(out[name], flush=True)

@@ -90,7 +90,10 @@ def test_max_sim_tensor_core(cuda_device, l, d, n, k):
     data, cent = torch.randn(l, d, n), torch.randn(l, d, k)
     osim, olab = K.max_sim(data.numpy(), cent.numpy())
     sim, lab = T.fn.max_sim(data.cuda(), cent.cuda(), exact=False)
+    sim_fast, lab_fast = T.fn.max_sim(data.cuda(), cent.cuda(), exact=False, exact_values=False)
     torch.cuda.synchronize()
+    assert torch.equal(lab, lab_fast)                                  # same labels, TF32-derived values
+    assert torch.allclose(sim_fast, sim, rtol=5e-3, atol=5e-2)
     sim, lab = sim.cpu().numpy(), lab.cpu().numpy()
     assert lab.min() >= 0 and lab.max() < k
     agree = (lab == olab).mean()

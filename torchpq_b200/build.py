@@ -26,7 +26,7 @@ def _assign(data: torch.Tensor, cent: torch.Tensor, exact: bool = True) -> torch
     arithmetic (used for encoding, so codes match the reference's); exact=False: TF32 tensor-core kernel where it
     applies (used inside the Lloyd iterations, where a label flip between near-equidistant centroids is harmless)."""
     from . import fn
-    return fn.max_sim(data.contiguous(), cent.contiguous(), "euclidean", exact=exact)[1]
+    return fn.max_sim(data.contiguous(), cent.contiguous(), "euclidean", exact=exact, exact_values=False)[1]
 
 
 def multi_kmeans(data: torch.Tensor, k: int, max_iter: int, tol: float = 1e-4, seed: int = 0) -> torch.Tensor:

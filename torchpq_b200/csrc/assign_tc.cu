@@ -104,6 +104,7 @@ struct TcParams {
   float* maxsims; int64_t* labels;
   const float* cent;             // for |c|^2 of padded columns nothing is read: TMA zero-fills
   float* dbg;                    // debug: raw accumulators of tile 0 of CTA 0, [128][256]
+  int exact_values;              // 1: maxsims recomputed exactly in fp32 for the chosen centroid; 0: 2*score - |x|^2 from the TF32 score
 };
 static float* g_tc_dbg = nullptr;
 
@@ -308,22 +309,36 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         if (lane == 0) mbar_arrive(&cand_empty[tb]);
         // exact fp32 similarity of the chosen centroid (max_sim.cu:78-98 arithmetic)
         // The swizzle term of box_off has period 4 in the row: four precomputed bases per operand, the row offset
-        // (e * 128) folds into the load's immediate after unrolling -> 2 LDS + FADD + FFMA per feature.
+        // (e * 128) folds into the load's immediate after unrolling.
         const uint8_t* xa = sA + s * (size_t)a_bytes + (row >> 5) * box_bytes;
-        const uint8_t* cb = sB + (besti >> 5) * box_bytes;
-        const uint8_t* xq[4]; const uint8_t* cq[4];
+        const uint8_t* xq[4];
         #pragma unroll
-        for (int r = 0; r < 4; ++r) { xq[r] = xa + box_off(r, row & 31); cq[r] = cb + box_off(r, besti & 31); }
+        for (int r = 0; r < 4; ++r) xq[r] = xa + box_off(r, row & 31);
         float acc = 0.f;
-        #pragma unroll 2
-        for (int e4 = 0; e4 < d; e4 += 4) {
+        if (P.exact_values) {
+          const uint8_t* cb = sB + (besti >> 5) * box_bytes;
+          const uint8_t* cq[4];
           #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const float xv = *reinterpret_cast<const float*>(xq[r] + e4 * 128);
-            const float cvv = *reinterpret_cast<const float*>(cq[r] + e4 * 128);
-            const float dif = xv - cvv;
-            acc = fmaf(-dif, dif, acc);
+          for (int r = 0; r < 4; ++r) cq[r] = cb + box_off(r, besti & 31);
+          #pragma unroll 2
+          for (int e4 = 0; e4 < d; e4 += 4) {
+            #pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const float xv = *reinterpret_cast<const float*>(xq[r] + e4 * 128);
+              const float cvv = *reinterpret_cast<const float*>(cq[r] + e4 * 128);   // random column: bank conflicts
+              const float dif = xv - cvv;
+              acc = fmaf(-dif, dif, acc);
+            }
           }
+        } else {
+          // -|x - c|^2 = 2 (<x,c> - |c|^2/2) - |x|^2 with the TF32 score; |x|^2 exactly, conflict-free row reads
+          float x2 = 0.f;
+          #pragma unroll 2
+          for (int e4 = 0; e4 < d; e4 += 4) {
+            #pragma unroll
+            for (int r = 0; r < 4; ++r) { const float xv = *reinterpret_cast<const float*>(xq[r] + e4 * 128); x2 = fmaf(xv, xv, x2); }
+          }
+          acc = fmaf(2.f, best, -x2);
         }
         const long long p = (long long)ti * TC_M + row;
         if (p < P.n) {
@@ -383,7 +398,7 @@ bool assign_tc_supported(int l, int d, long long n, int k, const void* data, con
          n < (1ll << 31) && (reinterpret_cast<uintptr_t>(data) & 15) == 0 && (reinterpret_cast<uintptr_t>(cent) & 15) == 0;
 }
 
-int launch_assign_tc(const float* data, const float* cent, int l, int d, long long n, int k,
+int launch_assign_tc(const float* data, const float* cent, int l, int d, long long n, int k, int exact_values,
                      float* maxsims, int64_t* labels, cudaStream_t st) {
   CUtensorMap mx, mc;
   if (int rc = make_map(&mx, data, l, d, n)) return rc;
@@ -391,7 +406,7 @@ int launch_assign_tc(const float* data, const float* cent, int l, int d, long lo
   TcParams P;
   P.l = l; P.d = d; P.n = (int)n; P.k = k; P.kpad = (k + 31) / 32 * 32;
   P.tiles_per_l = (int)((n + TC_M - 1) / TC_M);
-  P.maxsims = maxsims; P.labels = labels; P.cent = cent; P.dbg = g_tc_dbg;
+  P.maxsims = maxsims; P.labels = labels; P.cent = cent; P.dbg = g_tc_dbg; P.exact_values = exact_values;
   const size_t box = (size_t)d * 128;
   const size_t smem = (size_t)(P.kpad / 32) * box + (size_t)TC_STAGES * 4 * box + 12 * 1024 + 256 * 4 + 32 * 8 + 8192 + 1024;
   TPQ_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -237,7 +237,7 @@ pq_decode_kernel(const float* __restrict__ codebook, const uint8_t* __restrict__
 
 namespace tpq {
 bool assign_tc_supported(int l, int d, long long n, int k, const void* data, const void* cent);
-int launch_assign_tc(const float* data, const float* cent, int l, int d, long long n, int k,
+int launch_assign_tc(const float* data, const float* cent, int l, int d, long long n, int k, int exact_values,
                      float* maxsims, int64_t* labels, cudaStream_t st);
 }
 
@@ -250,8 +250,8 @@ extern "C" int tpq_max_sim(const float* data, const float* centroids, int l, int
   TPQ_REQUIRE(n <= 0x7fffffffll - MS_B && l <= 65535, "tpq_max_sim: n or l too large");
   TPQ_REQUIRE(metric == TPQ_METRIC_EUCLIDEAN || metric == TPQ_METRIC_COSINE, "tpq_max_sim: unsupported metric %d", metric);
   if (n == 0) return TPQ_OK;
-  if (!exact && metric == TPQ_METRIC_EUCLIDEAN && assign_tc_supported(l, d, n, k, data, centroids))
-    return launch_assign_tc(data, centroids, l, d, n, k, maxsims, labels, (cudaStream_t)stream);
+  if (exact != 1 && metric == TPQ_METRIC_EUCLIDEAN && assign_tc_supported(l, d, n, k, data, centroids))
+    return launch_assign_tc(data, centroids, l, d, n, k, exact == 2 ? 1 : 0, maxsims, labels, (cudaStream_t)stream);
   dim3 grid((unsigned)((n + MS_B - 1) / MS_B), l);
   if (metric == TPQ_METRIC_EUCLIDEAN)
     max_sim_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(data, centroids, d, (int)n, k, maxsims, labels);

@@ -92,16 +92,17 @@ class IVFPQTopk:
         return values, address
 
 
-def max_sim(data, centroids, distance="euclidean", exact=True):
+def max_sim(data, centroids, distance="euclidean", exact=True, exact_values=True):
     """MultiKMeans.get_labels / MaxSimCuda(dim=2): data [l, d, n], centroids [l, d, k] ->
-    (maxsims [l, n] f32, labels [l, n] i64).  exact=False lets the TF32 tensor-core kernel run where it applies."""
+    (maxsims [l, n] f32, labels [l, n] i64).  exact=False lets the TF32 tensor-core kernel run where it applies;
+    exact_values then selects exact fp32 maxsims for the chosen centroid (True) or TF32-derived ones (False, faster)."""
     a, b = _cuda_f32(data, "data"), _cuda_f32(centroids, "centroids")
     assert a.dim() == 3 and b.dim() == 3 and a.shape[:2] == b.shape[:2]
     l, d, n = a.shape
     k = b.shape[2]
     sims = torch.empty(l, n, dtype=torch.float32, device=a.device)
     labels = torch.empty(l, n, dtype=torch.long, device=a.device)
-    check(lib.tpq_max_sim(ptr(a), ptr(b), l, d, n, k, _lib.METRIC[distance], int(bool(exact)), ptr(sims), ptr(labels),
+    check(lib.tpq_max_sim(ptr(a), ptr(b), l, d, n, k, _lib.METRIC[distance], 1 if exact else (2 if exact_values else 0), ptr(sims), ptr(labels),
                           _lib.current_stream(a.device)))
     return sims, labels
 
