@@ -59,8 +59,10 @@ __global__ void __launch_bounds__(256)
 coarse_gemm_kernel(const float* __restrict__ x, const float* __restrict__ cb,
                    const float* __restrict__ xn, const float* __restrict__ cn,
                    int d, int nq, int C, float* __restrict__ sims) {
-  __shared__ __align__(16) float As[GK][GB];
-  __shared__ __align__(16) float Bs[GK][GB];
+  // two shared-memory stages; the next K-slab is fetched into registers while the current one is multiplied,
+  // so there is one barrier per slab and the global-load latency hides behind 16 x 64 FMAs per thread
+  __shared__ __align__(16) float As[2][GK][GB];
+  __shared__ __align__(16) float Bs[2][GK][GB];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int q0 = blockIdx.y * GB, c0 = blockIdx.x * GB;
   float acc[8][8];
@@ -69,23 +71,36 @@ coarse_gemm_kernel(const float* __restrict__ x, const float* __restrict__ cb,
     #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < d; k0 += GK) {
-    // 16 x 128 floats per operand = 2048 elements / 256 threads = 8 each
+  float ra[8], rb[8];
+  auto fetch = [&](int k0) {                              // 16 x 128 floats per operand = 8 per thread
     #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      int e = r * 256 + tid;
-      int kk = e >> 7, col = e & 127;
-      int gk = k0 + kk;
-      As[kk][col] = (gk < d && q0 + col < nq) ? x[(size_t)gk * nq + q0 + col] : 0.f;
-      Bs[kk][col] = (gk < d && c0 + col < C) ? cb[(size_t)gk * C + c0 + col] : 0.f;
+      const int e = r * 256 + tid, kk = e >> 7, col = e & 127, gk = k0 + kk;
+      ra[r] = (gk < d && q0 + col < nq) ? __ldg(x + (size_t)gk * nq + q0 + col) : 0.f;
+      rb[r] = (gk < d && c0 + col < C) ? __ldg(cb + (size_t)gk * C + c0 + col) : 0.f;
     }
-    __syncthreads();
+  };
+  auto stash = [&](int buf) {
+    #pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = r * 256 + tid, kk = e >> 7, col = e & 127;
+      As[buf][kk][col] = ra[r];
+      Bs[buf][kk][col] = rb[r];
+    }
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int cur = 0;
+  for (int k0 = 0; k0 < d; k0 += GK) {
+    const bool more = k0 + GK < d;
+    if (more) fetch(k0 + GK);
     #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
-      float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
-      float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      float4 a0 = *reinterpret_cast<const float4*>(&As[cur][kk][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[cur][kk][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][kk][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][kk][64 + tx * 4]);
       float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       #pragma unroll
@@ -93,7 +108,11 @@ coarse_gemm_kernel(const float* __restrict__ x, const float* __restrict__ cb,
         #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
-    __syncthreads();
+    if (more) {
+      stash(cur ^ 1);                                       // the other stage was last read one iteration ago
+      __syncthreads();
+      cur ^= 1;
+    }
   }
   #pragma unroll
   for (int i = 0; i < 8; ++i) {
