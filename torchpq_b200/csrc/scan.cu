@@ -13,11 +13,17 @@
 //   * one PRMT builds the whole address: byte 1 = the code byte, byte 0 = the lane's
 //     precomputed slot offset, bytes 2..3 = sign-replicated zero; the half-group and
 //     group offsets are LDS immediates.  Inner loop = PRMT + LDS + FADD per code byte.
-//   * each warp streams whole 32-vector blocks with coalesced 128-bit loads, software
-//     pipelined one block ahead; top-k is threshold-filtered per warp (WarpTopK) against
-//     a CTA-wide k-th-best, lists tree-merged at the end.
+//   * the LUT itself is built by the CTA, in place, from the L2-resident transposed codebook (d/M in
+//     {1,2,4}; otherwise it is staged through HBM by lut_scan_kernel).
+//   * each warp streams whole 32-vector blocks with coalesced 128-bit loads in units of 64
+//     sub-quantizers, software pipelined one unit ahead (ping-pong register sets).
+//   * top-k (CtaTopK, common.cuh): one compare against the CTA-wide running k-th best + one ballot per
+//     block; survivors are staged per warp and merged into the CTA's single sorted list under a lock;
+//     the threshold is bootstrapped, and the buffers are drained, by CTA-wide sorts.
+//   * RES variant: residual IVFPQ (per-cell LUT = query half + precomputed cell half).
 // Sub-quantizer sums are fp32 in four interleaved partial sums (exact for integer LUTs;
 // ~1e-7 relative otherwise -- the reference's m-ascending order lives in scan_ref.cu).
+// Environment knobs (experiments only, scripts/sweep_scan.py): TPQ_SCAN_CFG, TPQ_BOOT_R, TPQ_LUT_MODE.
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
