@@ -272,3 +272,35 @@ def test_argument_errors(cuda_device):
     ix.n_probe = 9                                              # > n_cells
     with pytest.raises(AssertionError):
         ix.search(queries(3).cuda(), k=1)
+
+
+def test_patch_reference_shaped_object(cuda_device):
+    """torchpq_b200.patch() on an object that only has the REFERENCE class's attributes (no torchpq_b200 base
+    class): index.search then runs the sm_100a path and matches the oracle."""
+    import torchpq_b200 as T
+
+    class Codec:                                   # what torchpq's VQCodec / PQCodec expose to search
+        def __init__(self, cb):
+            self.codebook, self.is_trained = cb, True
+
+    class RefShaped:                               # attribute names of torchpq.index.IVFPQIndex
+        def search(self, x, k=1):
+            raise RuntimeError("CuPy path")
+
+    st, queries = B.integer_state(64, 16, 16, 4000, seed=4, lo=-6, hi=7)
+    st.n_probe = 5
+    g = lambda a: torch.as_tensor(a).cuda().contiguous()
+    ref = RefShaped()
+    ref.d_vector, ref.n_subvectors, ref.n_cells, ref.distance, ref.device = 64, 16, 16, "euclidean", "cuda:0"
+    ref._storage, ref._is_empty, ref._cell_start = g(st.storage), g(st.is_empty), g(st.cell_start)
+    ref._cell_size, ref._address2id = g(st.cell_size), g(st.address2id)
+    ref.vq_codec, ref.pq_codec = Codec(g(st.vq_codebook)), Codec(g(st.pq_codebook))
+    ref.n_probe, ref.use_smart_probing, ref.smart_probing_temperature = 5, True, 30.0
+    T.patch(ref)
+    x = queries(30)
+    ov, oi, oa = O.search(st, x, k=12, return_address=True)
+    v, i, a = ref.search(x.cuda(), k=12, return_address=True)
+    assert np.array_equal(v.cpu().numpy(), ov) and np.array_equal(a.cpu().numpy(), oa) and np.array_equal(i.cpu().numpy(), oi)
+    T.unpatch(ref)
+    with pytest.raises(RuntimeError):
+        ref.search(x.cuda(), k=12)
