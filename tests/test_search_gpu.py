@@ -304,3 +304,16 @@ def test_patch_reference_shaped_object(cuda_device):
     T.unpatch(ref)
     with pytest.raises(RuntimeError):
         ref.search(x.cuda(), k=12)
+
+
+@pytest.mark.parametrize("M,d", [(96, 96), (160, 320), (192, 192), (100, 300)])
+def test_wide_codes_unit_pipeline(cuda_device, M, d):
+    """M = 96 / 160 / 192 / 100: two or three 64-sub-quantizer units per block (odd and even unit counts, a short last
+    unit, padding sub-quantizers), 16-warp CTAs, fused (d/M = 1, 2) and staged (d/M = 3) LUTs."""
+    st, queries = B.integer_state(d, M, 8, 3000, seed=M, lo=-3, hi=4)
+    st.n_probe, st.use_smart_probing = 4, True
+    x = queries(24)
+    ov, oi, oa = O.search(st, x, k=50, return_address=True)
+    ix = make_index(st)
+    v, i, a = ix.search(x.cuda(), k=50, return_address=True)
+    assert np.array_equal(v.cpu().numpy(), ov) and np.array_equal(a.cpu().numpy(), oa) and np.array_equal(i.cpu().numpy(), oi)
