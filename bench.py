@@ -406,6 +406,19 @@ def main():
         except Exception:
             traffic = None
 
+    # sharded run: does the cell-sharded search (all ranks, NCCL) return exactly what the unsharded index returns?
+    sharded_ok = None
+    if world > 1:
+        try:
+            v_s, i_s = tdist.sharded_search(index, xs_dev[0], k)
+            torch.cuda.synchronize()
+            if rank == 0:
+                index.set_shard(0, 1)
+                v_u, i_u = index.search(xs_dev[0], k=k)
+                sharded_ok = bool(torch.equal(v_s, v_u) and torch.equal(i_s, i_u))
+                index.set_shard(rank, world)
+        except Exception as e:                                       # report, never take the number down
+            sharded_ok = f"check failed: {e!r}"
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -447,7 +460,7 @@ def main():
         "config": {"workload": f"{args.workload}: {desc}", "n_query_per_step": nq, "index_sharding": f"cells mod {world}",
                    "use_smart_probing": index.use_smart_probing,
                    "l2_policy": "inputs larger than L2 (code store >= 640 MB vs 126 MB L2; 4 rotating query batches)"},
-        "recall_at_100": rec,
+        "recall_at_100": rec, "sharded_equals_unsharded": sharded_ok,
         "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": d * nq * 4, "d2h_bytes_per_step": nq * k * 12,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_per_step * args.steps,

@@ -85,3 +85,84 @@ def test_key_packing_roundtrip_and_order():
     order = np.argsort(k)[::-1]
     expect = np.lexsort((a, -v.astype(np.float64)))
     assert np.array_equal(v[order], v[expect])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# torchpq_b200.dist.sharded_search itself (its collective plumbing: query-split coarse probe, packed all-gather of
+# cells / n_probe_list / coarse similarities, key all-gather, merge), with the CUDA ops replaced by the oracle.
+# ---------------------------------------------------------------------------------------------------------------
+class _OracleIndex:
+    """Stands in for IVFPQIndex on CPU: same attributes / methods sharded_search touches."""
+
+    def __init__(self, st, rank, world):
+        self.st, self.rank, self.world = st, rank, world
+        self.n_probe, self.distance = st.n_probe, st.distance
+        self.use_smart_probing, self.smart_probing_temperature = st.use_smart_probing, st.smart_probing_temperature
+        self.vq_codec = type("C", (), {"codebook": torch.from_numpy(st.vq_codebook)})()
+        self._address2id = torch.from_numpy(st.address2id)
+
+    def search_cells(self, x, cells, base_sims=None, n_probe_list=None, k=1, return_keys=False):
+        from oracle import ivfpq_oracle as O
+        cn = cells.numpy()
+        size = self.st.cell_size[cn].copy()
+        size[(cn % self.world) != self.rank] = 0
+        lut = O.precompute_adc(x, torch.from_numpy(self.st.pq_codebook), self.st.distance).numpy()
+        v, a = O.ivfpq_topk(self.st.storage, lut, self.st.is_empty, self.st.cell_start[cn], size, n_probe_list.numpy(), k)
+        return None, None, torch.from_numpy(pack_keys(v, a).view(np.int64))
+
+
+def _cpu_coarse_probe(x, vq_codebook, n_probe, smart, temperature):
+    from oracle import ivfpq_oracle as O
+    sims = O.negative_squared_l2(x, vq_codebook).contiguous()
+    s, c = O.topk_desc(sims, n_probe)
+    npl = O.smart_probing(s, n_probe, temperature) if (smart and n_probe > 1) else torch.zeros(x.shape[1], dtype=torch.long) + n_probe
+    return s, c, npl
+
+
+def _cpu_merge(keys_all, address2id):
+    k = keys_all.shape[2]
+    allk = keys_all.numpy().view(np.uint64).transpose(1, 0, 2).reshape(keys_all.shape[1], -1)
+    top = np.ascontiguousarray(np.sort(allk, axis=1)[:, ::-1][:, :k])
+    v, a = unpack_keys(top)
+    ids = np.where(a >= 0, address2id.numpy()[np.maximum(a, 0)], -1)
+    return torch.from_numpy(v), torch.from_numpy(ids), torch.from_numpy(a)
+
+
+def worker_sharded_search(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import ivfpq_oracle as O, build_state as B
+    from torchpq_b200 import dist as tdist
+    tdist.fn.coarse_probe = _cpu_coarse_probe            # the only CUDA ops on this path
+    tdist.fn.merge_topk = _cpu_merge
+    st, queries = B.integer_state(32, 8, 16, 3000, seed=5)
+    st.n_probe, st.use_smart_probing = 6, True
+    x, k = queries(21), 12                                # 21 queries over 2 ranks: uneven split, padded slice
+    fv, fi, fa = O.search(st, x, k=k, return_address=True)
+    ok = True
+    for split in (True, False):
+        ix = _OracleIndex(st, rank, world)
+        if not split:                                     # replicated coarse probe: search() = coarse + search_cells
+            def search(xx, k=1, return_keys=False, _ix=ix):
+                s, c, npl = _cpu_coarse_probe(xx, _ix.vq_codec.codebook, _ix.n_probe, True, 30.0)
+                return _ix.search_cells(xx, c, base_sims=s, n_probe_list=npl, k=k, return_keys=True)
+            ix.search = search
+        v, ids, a = tdist.sharded_search(ix, x, k, return_address=True, split_coarse=split)
+        ok = ok and np.array_equal(v.numpy(), fv) and np.array_equal(a.numpy(), fa) and np.array_equal(ids.numpy(), fi)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_sharded_search_plumbing_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=worker_sharded_search, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
