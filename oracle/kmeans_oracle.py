@@ -62,3 +62,22 @@ def pq_decode(codebook, code):
     for m in range(M):
         out[m] = codebook[m][:, code[m]]
     return out.reshape(M * dsub, n)
+
+
+def fit(data, centroids0, max_iter, tol=1e-4):
+    """MultiKMeans.fit for one redo from given initial centroids, euclidean (clustering/MultiKMeans.py:431-441):
+    labels = arg-max similarity, new centroids = member means, error = sum((new - old)^2), stop when error <= tol.
+    -> (centroids, labels of the last assignment, inertia = mean(-maxsims), iterations)."""
+    cent = np.asarray(centroids0, np.float32)
+    k = cent.shape[2]
+    n_iter = 0
+    for _ in range(max_iter):
+        sims, labels = max_sim(data, cent, "euclidean")
+        new = compute_centroids(data, labels, k)
+        diff = (new - cent).astype(np.float32)
+        error = float((diff * diff).astype(np.float32).sum(dtype=np.float32))
+        cent = new
+        n_iter += 1
+        if error <= tol:
+            break
+    return cent, labels, float((-sims).mean()), n_iter

@@ -104,3 +104,32 @@ def test_max_sim_tensor_core(cuda_device, l, d, n, k):
     if bad.any():
         rel = (osim[bad] - sim[bad]) / np.abs(osim[bad])
         assert rel.min() >= 0 and rel.max() < 5e-3
+
+
+def test_fit_matches_oracle_loop(cuda_device):
+    """build.fit = the reference's MultiKMeans.fit loop (clustering/MultiKMeans.py:415-453): from identical initial
+    centroids on integer-valued data (sums of members are exact in fp32, so every Lloyd step is order-independent)
+    the exact-assignment GPU loop and the CPU restatement agree bit for bit: centroids, labels, iteration count."""
+    from torchpq_b200 import build
+    rng = np.random.default_rng(3)
+    data = torch.from_numpy(rng.integers(-8, 9, (3, 4, 3000)).astype(np.float32))
+    c0 = data[:, :, rng.choice(3000, 16, replace=False)].clone()
+    ocent, olab, oinertia, oit = K.fit(data.numpy(), c0.numpy(), max_iter=12, tol=1e-4)
+    cent, lab, inertia, it = build.fit(data.cuda().contiguous(), 16, max_iter=12, tol=1e-4, centroids=c0.cuda(), exact=True)
+    assert it == oit
+    assert np.array_equal(lab.cpu().numpy(), olab)
+    assert np.allclose(cent.cpu().numpy(), ocent, rtol=1e-6, atol=1e-6)
+    assert abs(inertia - oinertia) <= 1e-4 * max(1.0, abs(oinertia))
+
+
+def test_fit_stops_on_sum_of_squares_and_picks_best_redo(cuda_device):
+    """error = sum((new - old)^2) <= tol stops the loop (not a mean shift); with n_redo > 1 the lowest-inertia run wins."""
+    from torchpq_b200 import build
+    torch.manual_seed(0)
+    centers = torch.randn(1, 8, 4) * 20
+    data = (centers[:, :, torch.randint(0, 4, (2000,))] + torch.randn(1, 8, 2000)).cuda().contiguous()
+    cent, lab, inertia, it = build.fit(data, 4, max_iter=50, tol=1e-4, n_redo=1, seed=1)
+    assert it < 50                                                   # converged by the tolerance, not by max_iter
+    runs = [build.fit(data, 4, max_iter=50, tol=1e-4, n_redo=1, seed=s)[2] for s in (5, 6, 7)]
+    best = build.fit(data, 4, max_iter=50, tol=1e-4, n_redo=3, seed=5)[2]
+    assert abs(best - min(runs)) <= 1e-3 * abs(min(runs))

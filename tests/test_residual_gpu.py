@@ -60,3 +60,29 @@ def test_residual_train_add_search_and_decode(cuda_device):
     rec = ix.decode((codes, cells))
     err_res = (rec - base[:, :100]).norm() / base[:, :100].norm()
     assert err_res < 0.6                                          # residual quantisation reconstructs the vectors
+
+
+def test_residual_probe_list_zero_and_nan(cuda_device):
+    """n_probe_list entries 0 and INT64_MIN (the NaN-derived value, IVFPQIndex.py:508-510): the residual kernel's loop is
+    `for cCell < nProbe` with nProbe read as a 32-bit int (ivfpq_topk.cu:1080), so both scan nothing -> (-inf, -1)
+    rows; other rows are unaffected."""
+    torch.manual_seed(11)
+    base = torch.randn(32, 4000)
+    st = B.build_state_residual(base, 8, 16)
+    st.n_probe, st.use_smart_probing = 6, False
+    x = torch.randn(32, 12)
+    xx, sims, cells, npl = O.coarse_probe(st, x)
+    npl = npl.clone()
+    npl[0], npl[1], npl[2], npl[3] = 0, O.INT64_MIN, 1, 7          # 7 > n_probe: clamped
+    cn = cells.numpy()
+    p1, p2 = O.residual_parts(xx, torch.from_numpy(st.vq_codebook), torch.from_numpy(st.pq_codebook))
+    ov, oa = O.ivfpq_topk_residual_precomputed(st.storage, p1.numpy(), p2.numpy(), cn, sims.numpy(), st.is_empty,
+                                               st.cell_start[cn], st.cell_size[cn], npl.numpy(), 15)
+    ix = make_residual_index(st)
+    v, i, a = ix.search_cells(x.cuda(), cells.cuda(), base_sims=sims.cuda(), n_probe_list=npl.cuda(), k=15, return_address=True)
+    v, a = v.cpu().numpy(), a.cpu().numpy()
+    assert np.isinf(v[:2]).all() and (a[:2] == -1).all() and (i[:2].cpu().numpy() == -1).all()
+    assert np.isinf(ov[:2]).all()
+    assert np.allclose(v[2:], ov[2:], rtol=1e-3, atol=0)
+    tf = np.all(np.diff(ov[2:], axis=1) != 0, axis=1)
+    assert (a[2:][tf] == oa[2:][tf]).mean() >= 0.995

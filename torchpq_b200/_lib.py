@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtpq_b200.so")
+# TPQ_B200_LIB: load another build of the same ABI (scripts/ use it for the -DTPQ_DEBUG_KNOBS experiment build)
+LIB_PATH = os.environ.get("TPQ_B200_LIB") or os.path.join(_HERE, "libtpq_b200.so")
 
 TPQ_OK = 0
 TPQ_ERR_BAD_ARG = -1

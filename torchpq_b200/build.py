@@ -14,7 +14,8 @@ measured path.  Semantics followed:
     CellContainer.add       torchpq/container/CellContainer.py:313-367 (ioa, expand loop, write address
                             = ioa-th empty slot of the cell, get_write_address_v2.cu:9-41)
 Unlike the reference (unseeded np.random.choice, MultiKMeans.py:277-283) initial centroids come
-from a seeded torch.Generator, so training is reproducible.
+from a seeded torch.Generator: two runs start from the same centroids.  (Codebooks are reproducible to fp32
+rounding, not bit for bit: the centroid update accumulates per-tile partial sums with float atomics.)
 """
 from __future__ import annotations
 
@@ -29,23 +30,59 @@ def _assign(data: torch.Tensor, cent: torch.Tensor, exact: bool = True) -> torch
     return fn.max_sim(data.contiguous(), cent.contiguous(), "euclidean", exact=exact, exact_values=False)[1]
 
 
-def multi_kmeans(data: torch.Tensor, k: int, max_iter: int, tol: float = 1e-4, seed: int = 0) -> torch.Tensor:
-    """l independent k-means over data [l, d, n] -> centroids [l, d, k]."""
+def _init_centroids(data: torch.Tensor, k: int, seed: int) -> torch.Tensor:
+    """MultiKMeans.initialize_centroids, init_mode="random" (MultiKMeans.py:271-283): k distinct data points, the same
+    columns for every sub-quantizer -- from a seeded generator instead of the reference's unseeded np.random.choice."""
     l, d, n = data.shape
     gen = torch.Generator(device="cpu").manual_seed(seed)
     pick = torch.randperm(n, generator=gen)[:k].to(data.device)
     cent = data[:, :, pick].clone()
-    if cent.shape[2] < k:
+    if cent.shape[2] < k:                                              # fewer points than clusters
         cent = torch.cat([cent, torch.zeros(l, d, k - cent.shape[2], device=data.device)], dim=2)
-    from . import fn
-    for _ in range(max_iter):
-        lab = _assign(data, cent, exact=False)
-        new = fn.compute_centroids(data, lab, k)
-        shift = (new - cent).pow(2).sum(dim=1).sqrt().mean()
-        cent = new
-        if float(shift) < tol:
-            break
     return cent
+
+
+def fit(data: torch.Tensor, k: int, max_iter: int, tol: float = 1e-4, n_redo: int = 1, seed: int = 0,
+        centroids: torch.Tensor | None = None, distance: str = "euclidean", exact: bool = False):
+    """MultiKMeans.fit (clustering/MultiKMeans.py:415-453; KMeans.fit, KMeans.py:399-438, is the l = 1 case):
+    l independent k-means over data [l, d, n].  Per redo: Lloyd iterations until `error = sum((new - old)^2) <= tol`
+    (calculate_error, :143-149 -- a SUM of squares over all l*d*k entries, not a mean shift) or max_iter; the redo
+    with the lowest inertia = mean(-maxsims) (:151-152) wins.  -> (centroids [l, d, k], labels [l, n], inertia, n_iter).
+    As in the reference the returned labels are those of the last assignment, i.e. relative to the centroids BEFORE
+    the final update.  exact=True: the reference's fp32 assignment arithmetic bit for bit (max_sim.cu:78-98);
+    exact=False: TF32 tensor-core assignment where the shape allows (labels can differ between near-equidistant
+    centroids only)."""
+    from . import fn
+    assert data.dim() == 3 and data.is_contiguous(), "use .contiguous()"                  # MultiKMeans.py:421
+    assert distance in ("euclidean", "cosine")
+    best = None
+    best_inertia = 1e32
+    for redo in range(n_redo):
+        cent = centroids if (centroids is not None and redo == 0) else _init_centroids(data, k, seed + redo)
+        n_iter = 0
+        for _ in range(max_iter):
+            if distance == "cosine":                                    # get_labels, MultiKMeans.py:314-333
+                dn = data / (data.norm(dim=-2, keepdim=True) + 1e-8)
+                cn = cent / (cent.norm(dim=-2, keepdim=True) + 1e-8)
+                maxsims, labels = fn.max_sim(dn.contiguous(), cn.contiguous(), "cosine", exact=True)
+            else:
+                maxsims, labels = fn.max_sim(data, cent.contiguous(), "euclidean", exact=exact, exact_values=n_redo > 1)
+            new = fn.compute_centroids(data, labels, k)
+            error = (new - cent).pow(2).sum()
+            cent = new
+            n_iter += 1
+            if float(error) <= tol:                                     # one host sync per iteration, as in the reference
+                break
+        inertia = float((-maxsims).mean())
+        if inertia < best_inertia:
+            best, best_inertia = (cent, labels, inertia, n_iter), inertia
+    return best
+
+
+def multi_kmeans(data: torch.Tensor, k: int, max_iter: int, tol: float = 1e-4, seed: int = 0,
+                 distance: str = "euclidean") -> torch.Tensor:
+    """l independent k-means over data [l, d, n] -> centroids [l, d, k] (fit with the reference's defaults)."""
+    return fit(data, k, max_iter, tol=tol, n_redo=1, seed=seed, distance=distance)[0]
 
 
 def train(index, x: torch.Tensor, seed: int = 0, vq_iters: int = 15, pq_iters: int = 25):
@@ -58,7 +95,7 @@ def train(index, x: torch.Tensor, seed: int = 0, vq_iters: int = 15, pq_iters: i
     if getattr(index, "pq_use_residual", False):                       # IVFPQIndex.py:248-256: PQ learns x - vq(x)
         x = x - vq[:, _assign(x[None].contiguous(), vq[None])[0]]
     sub = x.reshape(index.n_subvectors, index.d_subvector, x.shape[1]).contiguous()
-    pq = multi_kmeans(sub, 256, pq_iters, seed=seed + 1).contiguous()
+    pq = multi_kmeans(sub, 256, pq_iters, seed=seed + 1, distance=index.distance).contiguous()   # PQCodec.py:27-32
     index.vq_codec.set_codebook(vq)
     index.pq_codec.set_codebook(pq)
     index._state_changed()
@@ -126,7 +163,13 @@ def container_add(index, codes: torch.Tensor, cells: torch.Tensor, ids=None, ret
         ids = ids.to(dev)
     ioa = _ioa(cells)
     while True:
-        free = index._cell_capacity[cells] - index._cell_size[cells] - (ioa + 1)
+        # free slots of a cell = capacity - LIVE items.  Without holes live == _cell_size and this is the reference's
+        # `capacity - cell_size - (ioa + 1)` (CellContainer.py:338-341); with holes left by remove() it stops the cell
+        # from expanding while it still has room (and _cell_size, a high-water mark here, from inflating).
+        occupied = torch.cumsum((index._is_empty == 0).to(torch.long), 0)
+        occupied = torch.cat([occupied.new_zeros(1), occupied])
+        live = occupied[index._cell_start + index._cell_capacity] - occupied[index._cell_start]
+        free = index._cell_capacity[cells] - live[cells] - (ioa + 1)
         need = cells[free < 0].unique()
         if need.shape[0] == 0:
             break
@@ -140,8 +183,9 @@ def container_add(index, codes: torch.Tensor, cells: torch.Tensor, ids=None, ret
     if n:
         index._max_id = max(index._max_id, int(ids.max().item()))
     index._is_empty[write] = 0
-    uc, cnt = cells.unique(return_counts=True)
-    index._cell_size[uc] += cnt
+    # _cell_size = extent the scan must cover = highest occupied slot + 1 (== old + count when the cell has no holes)
+    extent = write - index._cell_start[cells] + 1
+    index._cell_size.scatter_reduce_(0, cells, extent, reduce="amax", include_self=True)
     index._state_changed()
     return (ids, write) if return_address else ids
 

@@ -11,10 +11,11 @@
 
 namespace tpq {
 
-// Column reductions over a [d, n] matrix.  A CTA owns 32 columns; its 32 x 8 threads split the rows eight ways
+// Column reductions over a [d, n] matrix.  A CTA owns 32 columns; its 32 x 32 threads split the rows 32 ways
 // (coalesced 128-byte row segments), partial sums meet in shared memory.  Row-group partials are combined in
-// ascending group order, so the result is deterministic.
-constexpr int CR_G = 8;     // row groups per CTA
+// ascending group order, so the result is deterministic.  (32 row groups rather than round 1's 8: a 1000-query
+// batch is only 32 CTAs, so at d = 960 the per-thread row loop was the whole latency of the cosine step.)
+constexpr int CR_G = 32;    // row groups per CTA
 __device__ __forceinline__ float col_sumsq(const float* __restrict__ x, int d, int n, int j, int g, float (*part)[33], bool fma) {
   float s = 0.f;
   if (j < n) {

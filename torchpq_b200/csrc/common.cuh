@@ -48,54 +48,155 @@ __device__ __forceinline__ float    key_score(uint64_t k) { return ord_to_score(
 __device__ __forceinline__ uint32_t key_addr(uint64_t k)  { return 0xFFFFFFFFu - (uint32_t)k; }
 
 #ifdef __CUDACC__
-// ----------------------------------------------------------------------------- warp-cooperative sorted lists in shared memory
-// All routines are called by a full warp with warp-uniform arguments.
+// ----------------------------------------------------------------------------- bitonic networks in registers
+// A warp holds a sequence of 32*R keys as x[r] = element r*32 + lane.  Compare-exchanges at distance >= 32 are
+// register-to-register inside a thread; smaller distances are one SHFL.64 per key -- a quarter of the shared-memory
+// traffic of the same stage done through LDS/STS pairs, and free of bank conflicts (the strided 64-bit accesses of the
+// small-distance stages were the bulk of the scan kernel's bank conflicts in round 1, profiles/r01_summary.md).
+__device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int m) {
+  return (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v, m);
+}
+__device__ __forceinline__ uint64_t key_max(uint64_t a, uint64_t b) { return a > b ? a : b; }
+__device__ __forceinline__ uint64_t key_min(uint64_t a, uint64_t b) { return a < b ? a : b; }
 
-// Bitonic sort of a[0..n) (n a power of two >= 2), DESCENDING.
-__device__ __forceinline__ void warp_sort_desc(uint64_t* a, int n, int lane) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = lane; t < (n >> 1); t += 32) {
-        int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        int hi = lo + j;
-        bool desc = ((lo & k) == 0);
-        uint64_t x = a[lo], y = a[hi];
-        if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+// bitonic sequence -> sorted (descending, or ascending when ASC)
+template <int R, bool ASC = false>
+__device__ __forceinline__ void reg_merge(uint64_t (&x)[R], int lane) {
+  #pragma unroll
+  for (int j = 16 * R; j > 0; j >>= 1) {
+    if (j >= 32) {
+      const int dr = j >> 5;
+      #pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if ((r & dr) == 0) {
+          const uint64_t a = x[r], b = x[r | dr];
+          x[r]      = ASC ? key_min(a, b) : key_max(a, b);
+          x[r | dr] = ASC ? key_max(a, b) : key_min(a, b);
+        }
       }
-      __syncwarp();
+    } else {
+      const bool up = (lane & j) != 0;
+      #pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const uint64_t y = shfl_xor64(x[r], j);
+        x[r] = (up != ASC) ? key_min(x[r], y) : key_max(x[r], y);
+      }
     }
   }
 }
 
-// Sort a BITONIC sequence a[0..n) descending (the merge half of the network).
+// arbitrary sequence -> sorted (descending, or ascending when ASC)
+template <int R, bool ASC = false>
+__device__ __forceinline__ void reg_sort(uint64_t (&x)[R], int lane) {
+  #pragma unroll
+  for (int k = 2; k <= 32 * R; k <<= 1) {
+    #pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int dr = j >> 5;
+        #pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & dr) == 0) {
+            const bool desc = (((r * 32) & k) == 0) != ASC;        // k >= 64 here: the lane bits do not matter
+            const uint64_t a = x[r], b = x[r | dr];
+            x[r]      = desc ? key_max(a, b) : key_min(a, b);
+            x[r | dr] = desc ? key_min(a, b) : key_max(a, b);
+          }
+        }
+      } else {
+        const bool up = (lane & j) != 0;
+        #pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const bool desc = ((((r * 32) | lane) & k) == 0) != ASC;
+          const uint64_t y = shfl_xor64(x[r], j);
+          x[r] = (desc != up) ? key_max(x[r], y) : key_min(x[r], y);
+        }
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- warp-cooperative sorted lists in shared memory
+// All routines are called by a full warp with warp-uniform arguments.
+
+// Sort a BITONIC sequence a[0..n) in shared memory descending (n a power of two >= 32).  Distances >= 64 are
+// compare-exchanges between conflict-free runs of consecutive keys; the last six stages of every 64-key chunk run in
+// registers.
 __device__ __forceinline__ void warp_bitonic_merge_desc(uint64_t* a, int n, int lane) {
-  for (int j = n >> 1; j > 0; j >>= 1) {
+  for (int j = n >> 1; j >= 64; j >>= 1) {
     for (int t = lane; t < (n >> 1); t += 32) {
-      int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-      int hi = lo + j;
-      uint64_t x = a[lo], y = a[hi];
+      const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+      const int hi = lo + j;
+      const uint64_t x = a[lo], y = a[hi];
       if (x < y) { a[lo] = y; a[hi] = x; }
     }
     __syncwarp();
   }
+  if (n == 32) {
+    uint64_t x[1] = {a[lane]};
+    reg_merge<1>(x, lane);
+    a[lane] = x[0];
+  } else {
+    for (int c = 0; c < n; c += 64) {
+      uint64_t x[2] = {a[c + lane], a[c + 32 + lane]};
+      reg_merge<2>(x, lane);
+      a[c + lane] = x[0]; a[c + 32 + lane] = x[1];
+    }
+  }
+  __syncwarp();
 }
 
-// A[0..n) and B[0..nb) both sorted descending, nb <= n, n a power of two.
-// A <- the n largest of A u B, sorted descending.  B is left unspecified.
+// A[0..n) and B[0..nb) (shared memory) both sorted descending, nb <= n, both powers of two >= 32.
+// A <- the n largest of A u B, sorted descending.  B is left untouched.
 __device__ __forceinline__ void warp_merge_desc(uint64_t* A, int n, const uint64_t* B, int nb, int lane) {
   for (int t = lane; t < nb; t += 32) {
-    int i = n - nb + t;
-    uint64_t x = A[i], y = B[nb - 1 - t];
-    A[i] = x > y ? x : y;
+    const int i = n - nb + t;
+    A[i] = key_max(A[i], B[nb - 1 - t]);
   }
   __syncwarp();
   warp_bitonic_merge_desc(A, n, lane);
 }
 
+// Merge a run of 32*R keys held in registers, sorted ASCENDING (x[r] = element r*32 + lane), into the descending list
+// A[0..n) (n >= 32*R): A <- the n largest of A u run, sorted descending.
+template <int R>
+__device__ __forceinline__ void warp_merge_run(uint64_t* A, int n, const uint64_t (&x)[R], int lane) {
+  uint64_t* tail = A + (n - 32 * R);
+  if (n == 32 * R) {                                       // the whole list fits the registers
+    uint64_t y[R];
+    #pragma unroll
+    for (int r = 0; r < R; ++r) y[r] = key_max(tail[r * 32 + lane], x[r]);
+    reg_merge<R>(y, lane);
+    #pragma unroll
+    for (int r = 0; r < R; ++r) tail[r * 32 + lane] = y[r];
+    __syncwarp();
+    return;
+  }
+  #pragma unroll
+  for (int r = 0; r < R; ++r) tail[r * 32 + lane] = key_max(tail[r * 32 + lane], x[r]);
+  __syncwarp();
+  warp_bitonic_merge_desc(A, n, lane);
+}
+
+// In-place merge of two descending runs A[0..len), B[0..len) (len a power of two >= 32):
+//   top_only: A <- the len largest of A u B, descending (B clobbered);
+//   else:     A, B <- A u B sorted descending across (A then B).
+__device__ __forceinline__ void warp_merge_runs(uint64_t* A, uint64_t* B, int len, bool top_only, int lane) {
+  for (int t = lane; t < len; t += 32) {
+    const uint64_t a = A[t], b = B[len - 1 - t];
+    A[t] = key_max(a, b);
+    if (!top_only) B[len - 1 - t] = key_min(a, b);          // the low half, reversed: still bitonic
+  }
+  __syncwarp();
+  warp_bitonic_merge_desc(A, len, lane);
+  if (!top_only) warp_bitonic_merge_desc(B, len, lane);
+}
+
+constexpr int kTopkBuf = 64;      // staging-buffer entries per warp
+
 // Per-warp top-k selector: sorted list of KP keys + an unsorted staging buffer.
 // Candidates are appended with push(); when the buffer cannot take another full
 // warp's worth it is sorted and merged into the list.
-constexpr int kTopkBuf = 64;
 struct WarpTopK {
   uint64_t* list;   // [kp] descending
   uint64_t* buf;    // [kTopkBuf]
@@ -113,12 +214,16 @@ struct WarpTopK {
 
   __device__ __forceinline__ void flush(int lane) {
     if (cnt == 0) return;
-    for (int i = cnt + lane; i < kTopkBuf; i += 32) buf[i] = 0;
-    __syncwarp();
-    int nb = cnt <= 32 ? 32 : kTopkBuf;
-    warp_sort_desc(buf, nb, lane);
-    if (nb > kp) nb = kp;   // kp >= 32 always; only guards kp == 32 < 64
-    warp_merge_desc(list, kp, buf, nb, lane);
+    if (cnt <= 32) {
+      uint64_t x[1] = {lane < cnt ? buf[lane] : 0ull};
+      reg_sort<1, true>(x, lane);
+      warp_merge_run<1>(list, kp, x, lane);
+    } else {
+      uint64_t x[2] = {buf[lane], lane + 32 < cnt ? buf[lane + 32] : 0ull};
+      reg_sort<2, true>(x, lane);
+      if (kp == 32) { uint64_t y[1] = {x[1]}; warp_merge_run<1>(list, kp, y, lane); }   // the 32 largest of the run
+      else warp_merge_run<2>(list, kp, x, lane);
+    }
     cnt = 0;
   }
   // pass: this lane has a candidate.  Returns true if a flush happened (threshold may have risen).
@@ -133,25 +238,9 @@ struct WarpTopK {
   }
 };
 
-// Bitonic sort of a[0..n) (n a power of two), DESCENDING, by the whole CTA (every thread must call it).
-__device__ __forceinline__ void cta_sort_desc(uint64_t* a, int n) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
-        int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        int hi = lo + j;
-        bool desc = ((lo & k) == 0);
-        uint64_t x = a[lo], y = a[hi];
-        if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
-      }
-      __syncthreads();
-    }
-  }
-}
-
 // CTA-wide top-k selector: ONE sorted list of kp keys shared by all warps of the CTA (so its
 // k-th entry is the true running k-th best of everything merged so far), one staging buffer
-// per warp.  A warp whose buffer is more than half full sorts it privately, then takes the
+// per warp.  A warp whose buffer is more than half full sorts it privately (in registers), then takes the
 // CTA lock and merges it into the shared list; the other warps keep scanning against the
 // (slightly stale, always valid) threshold in *thr.  Exact: a candidate is only ever dropped
 // when k better ones are already in the list.
@@ -171,23 +260,34 @@ struct CtaTopK {
   }
   __device__ __forceinline__ uint64_t threshold() const { return *reinterpret_cast<volatile unsigned long long*>(thr); }
 
-  __device__ __forceinline__ void flush(int lane) {
-    if (cnt == 0) return;
-    for (int i = cnt + lane; i < kTopkBuf; i += 32) buf[i] = 0;
-    __syncwarp();
-    int nb = cnt <= 32 ? 32 : kTopkBuf;
-    warp_sort_desc(buf, nb, lane);
-    if (nb > kp) nb = kp;
+  template <int R>
+  __device__ __forceinline__ void merge_locked(const uint64_t (&x)[R], int lane) {
+    const uint64_t top = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)x[R - 1], 31);   // best staged key
+    if (top <= threshold()) return;                           // nothing staged still beats the k-th best (it only rises)
     if (lane == 0) { while (atomicCAS(lock, 0, 1) != 0) __nanosleep(20); }
     __syncwarp();
     __threadfence_block();
-    if (buf[0] > list[k - 1]) {                 // warp-uniform: anything left that still beats the k-th best?
-      warp_merge_desc(list, kp, buf, nb, lane);
+    if (top > list[k - 1]) {                                  // warp-uniform
+      warp_merge_run<R>(list, kp, x, lane);
       if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(thr) = list[k - 1];
     }
     __threadfence_block();
     __syncwarp();
     if (lane == 0) atomicExch(lock, 0);
+  }
+  __device__ __forceinline__ void flush(int lane) {
+    if (cnt == 0) return;
+    if (cnt <= 32) {
+      uint64_t x[1] = {lane < cnt ? buf[lane] : 0ull};
+      reg_sort<1, true>(x, lane);
+      merge_locked<1>(x, lane);
+    } else {
+      uint64_t x[2] = {buf[lane], lane + 32 < cnt ? buf[lane + 32] : 0ull};
+      reg_sort<2, true>(x, lane);
+      if (kp == 32) { uint64_t y[1] = {x[1]}; merge_locked<1>(y, lane); }
+      else merge_locked<2>(x, lane);
+    }
+    __syncwarp();
     cnt = 0;
   }
   __device__ __forceinline__ void push(bool pass, uint64_t key, int lane) {
@@ -198,39 +298,41 @@ struct CtaTopK {
     __syncwarp();
     if (cnt > kTopkBuf - 32) flush(lane);
   }
-  // Whole-CTA flush (every thread calls it): the staging buffers of all warps (`bufs`, nw * kTopkBuf entries,
-  // contiguous) are compacted, sorted together by the CTA and merged into the list once, instead of nw
-  // lock-serialised warp flushes.  Used to bootstrap the threshold and to drain the buffers at the end.  Only the
-  // smallest power of two that holds the live entries is sorted.  `scratch` is an int[nw + 1] in shared memory.
-  __device__ __forceinline__ void cta_flush(uint64_t* bufs, int* scratch, int nw, int lane, int warp) {
-    // compaction: every thread picks its (up to two) entries up into registers, then writes them at the warp's offset
-    const uint64_t e0 = lane < cnt ? buf[lane] : 0ull;
-    const uint64_t e1 = lane + 32 < cnt ? buf[lane + 32] : 0ull;
-    if (lane == 0) scratch[warp + 1] = cnt;
-    if (threadIdx.x == 0) scratch[0] = 0;
-    __syncthreads();
-    if (warp == 0) {                                                 // inclusive scan of the nw counts (nw <= 32)
-      int v = lane < nw ? scratch[lane + 1] : 0;
-      #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
-      if (lane < nw) scratch[lane + 1] = v;
+  // Whole-CTA bootstrap (every thread calls it; every warp has staged exactly 32*R keys, R = 1 or 2, zeros for
+  // missing vectors): each warp sorts its run in registers, the runs are merged pairwise in a log2(nw)-level tree
+  // (runs are capped at kp keys), and warp 0 merges the survivor into the list and publishes the threshold --
+  // log2(nw) + 2 barriers instead of a CTA-wide bitonic sort (45 barriers for 512 keys) or nw lock-serialised flushes.
+  // `bufs` = the nw staging buffers, contiguous, kTopkBuf keys apart.
+  __device__ __forceinline__ void cta_bootstrap(uint64_t* bufs, int nw, int R, int lane, int warp) {
+    int len;                                                         // run length per warp
+    if (R == 1) {
+      uint64_t x[1] = {buf[lane]};
+      reg_sort<1>(x, lane);
+      buf[lane] = x[0];
+      len = 32;
+    } else {
+      uint64_t x[2] = {buf[lane], buf[lane + 32]};
+      reg_sort<2>(x, lane);
+      buf[lane] = x[0]; buf[lane + 32] = x[1];
+      len = kp < 64 ? 32 : 64;                                      // kp == 32: only the top half can matter
     }
     __syncthreads();
-    const int total = scratch[nw], off0 = scratch[warp];
-    int nb = 32;
-    while (nb < total) nb <<= 1;                                     // <= nw * kTopkBuf by construction
-    if (lane < cnt) bufs[off0 + lane] = e0;
-    if (lane + 32 < cnt) bufs[off0 + lane + 32] = e1;
-    __syncthreads();
-    for (int i = total + threadIdx.x; i < nb; i += blockDim.x) bufs[i] = 0;
-    __syncthreads();
-    if (total > 0) {                                                 // CTA-uniform
-      cta_sort_desc(bufs, nb);
-      if (warp == 0) {
-        const int take = nb < kp ? nb : kp;
-        warp_merge_desc(list, kp, bufs, take, lane);
-        if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(thr) = list[k - 1];
+    for (int s = 1; s < nw; s <<= 1) {
+      const bool top_only = 2 * len > kp;
+      if ((warp & (2 * s - 1)) == 0 && warp + s < nw) {
+        uint64_t* A = bufs + (size_t)warp * kTopkBuf;
+        uint64_t* B = bufs + (size_t)(warp + s) * kTopkBuf;
+        warp_merge_runs(A, B, len, top_only, lane);
+        if (!top_only && B != A + len) {                             // 32-key runs: close the gap
+          for (int t = lane; t < len; t += 32) A[len + t] = B[t];
+        }
       }
+      if (!top_only) len <<= 1;
+      __syncthreads();
+    }
+    if (warp == 0) {
+      warp_merge_desc(list, kp, bufs, len, lane);
+      if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(thr) = list[k - 1];
     }
     cnt = 0;
     __syncthreads();

@@ -23,7 +23,8 @@
 //   * RES variant: residual IVFPQ (per-cell LUT = query half + precomputed cell half).
 // Sub-quantizer sums are fp32 in four interleaved partial sums (exact for integer LUTs;
 // ~1e-7 relative otherwise -- the reference's m-ascending order lives in scan_ref.cu).
-// Environment knobs (experiments only, scripts/sweep_scan.py): TPQ_SCAN_CFG, TPQ_BOOT_R, TPQ_LUT_MODE.
+// Experiment knobs (TPQ_SCAN_CFG, TPQ_BOOT_R, TPQ_LUT_MODE) and per-phase cycle counters exist only in the
+// -DTPQ_DEBUG_KNOBS build (make dbg -> libtpq_b200_dbg.so, used by scripts/); the product library reads no environment.
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -226,7 +227,7 @@ struct Scanner {
   }
 };
 
-struct ScanSmem { size_t lut, part1, seg_blk0, seg_addr0, seg_cell, seg_prefix, thr, lock, scratch, list, bufs, total; };
+struct ScanSmem { size_t lut, part1, seg_blk0, seg_addr0, seg_cell, seg_prefix, thr, lock, list, bufs, total; };
 static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp, bool residual = false) {
   ScanSmem s; size_t off = 0;
   s.lut = off;        off += (size_t)((MP + 63) / 64) * 65536;
@@ -238,7 +239,6 @@ static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp, bool residual = f
   off = align_up(off, 8);
   s.thr = off;        off += 8;
   s.lock = off;       off += 8;
-  s.scratch = off;    off += align_up((size_t)(nw + 1) * 4, 8);
   s.list = off;       off += (size_t)kp * 8;
   s.bufs = off;       off += (size_t)nw * kTopkBuf * 8;
   s.total = off;
@@ -258,6 +258,10 @@ struct ScanArgs {
   uint64_t* keys_out;             // [nq, S, k]
   int nq, q_base, n_probe, k, kp, S;
   int boot_r;                     // blocks per warp in the bootstrap (1 or 2)
+  int n_cells;                    // probe entries outside [0, n_cells) are treated as empty segments
+#ifdef TPQ_DEBUG_KNOBS
+  unsigned long long* phase;      // [8] summed clock64 deltas: prologue, bootstrap, scan, drain; [4] = CTAs
+#endif
 };
 
 // DSUB > 0: the CTA builds its query's LUT itself from the (L2-resident) transposed codebook -- no LUT
@@ -294,13 +298,18 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       int nb = 0;
       if (j < P) {
         const int64_t c = cq[j];
-        const int64_t s = A.cell_start[c];
-        const bool skip = (j > 0) && (s == A.cell_start[cq[j - 1]]);
-        const int b0 = A.cell_block_start[c];
+        const bool ok = c >= 0 && c < A.n_cells;            // caller-supplied probe lists (search_cells) are not trusted
+        const int64_t s = ok ? A.cell_start[c] : -1;
+        bool skip = !ok;
+        if (ok && j > 0) {
+          const int64_t cp = cq[j - 1];
+          skip = cp >= 0 && cp < A.n_cells && s == A.cell_start[cp];
+        }
+        const int b0 = ok ? A.cell_block_start[c] : 0;
         nb = skip ? 0 : A.cell_block_start[c + 1] - b0;
         seg_blk0[j] = b0;
         seg_addr0[j] = (uint32_t)s;
-        if constexpr (RES) seg_cell[j] = (int32_t)c;
+        if constexpr (RES) seg_cell[j] = ok ? (int32_t)c : 0;
       }
       int incl = nb;
       #pragma unroll
@@ -334,14 +343,20 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       a2[h] = s2;
     }
     float* lutf = reinterpret_cast<float*>(RES ? smem + L.part1 : lut);
-    #pragma unroll 8
+    #pragma unroll (DSUB >= 8 ? 2 : 8)
     for (int c = warp; c < 256; c += NW) {
       #pragma unroll
       for (int h = 0; h < NH; ++h) {
         const float* p = A.cbt + ((size_t)c * MP + 32 * h + lane) * DSUB;
         float pv[DSUB];
         if constexpr (DSUB == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); pv[0] = t.x; pv[1] = t.y; }
-        else if constexpr (DSUB == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w; }
+        else if constexpr (DSUB % 4 == 0) {
+          #pragma unroll
+          for (int i = 0; i < DSUB; i += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p + i));
+            pv[i] = t.x; pv[i + 1] = t.y; pv[i + 2] = t.z; pv[i + 3] = t.w;
+          }
+        }
         else { for (int i = 0; i < DSUB; ++i) pv[i] = __ldg(p + i); }
         float dot = 0.f, b2 = 0.f;
         #pragma unroll
@@ -353,6 +368,15 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       }
     }
   }
+#ifdef TPQ_DEBUG_KNOBS
+  long long t_ph = clock64();
+  auto phase_mark = [&](int i) {
+    if (A.phase && tid == 0) { const long long t = clock64(); atomicAdd(A.phase + i, (unsigned long long)(t - t_ph)); t_ph = t; }
+  };
+#define TPQ_PHASE(i) phase_mark(i)
+#else
+#define TPQ_PHASE(i) ((void)0)
+#endif
   Scanner<MP, NW> sc;
   sc.codes = A.codes; sc.valid = A.valid; sc.lut = lut;
   sc.seg_prefix = seg_prefix; sc.seg_blk0 = seg_blk0; sc.seg_addr0 = seg_addr0; sc.lane = lane;
@@ -368,6 +392,7 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
     sc.off[i] = v;
   }
   __syncthreads();
+  TPQ_PHASE(0);
 
   const int total = seg_prefix[P];
   const int b_begin = (int)(((int64_t)total * slice) / A.S);
@@ -376,7 +401,6 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   sc.seg = 0; sc.seg_lo = 0; sc.seg_hi = seg_prefix[1]; sc.seg_b0 = seg_blk0[0]; sc.seg_a0 = seg_addr0[0];
   CtaTopK& tk = sc.tk;
   uint64_t* bufs = reinterpret_cast<uint64_t*>(smem + L.bufs);
-  int* scratch = reinterpret_cast<int*>(smem + L.scratch);
   if constexpr (RES) {
     const float4* p1 = reinterpret_cast<const float4*>(smem + L.part1);
     float4* dst = reinterpret_cast<float4*>(lut);
@@ -394,14 +418,15 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       sc.base = A.base_sims[(size_t)q * A.n_probe + j];
       sc.run(b0 + warp, b1);
     }
-    tk.cta_flush(bufs, scratch, NW, lane, warp);
+    tk.flush(lane);
+    __syncthreads();
     uint64_t* outr = A.keys_out + (size_t)q * A.k;
     for (int i = tid; i < A.k; i += NW * 32) outr[i] = tk.list[i];
     return;
   }
-  // bootstrap: the first R blocks of every warp go to the list unfiltered through ONE CTA-wide sort, which
-  // establishes the threshold (k-th best of the first R * NW * 32 vectors) without R * NW lock-serialised flushes.
-  // R = 1 when that already yields k candidates (k <= 32 NW), else 2 (the staging buffers hold two blocks).
+  // bootstrap: the first R blocks of every warp go to the list unfiltered through one register sort per warp and a
+  // log2(NW)-level merge tree, which establishes the threshold (k-th best of the first R * NW * 32 vectors) without
+  // R * NW lock-serialised flushes.
   const int R = A.boot_r;
   {
     #pragma unroll 1
@@ -410,10 +435,17 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       tk.buf[r * 32 + lane] = (b < b_end) ? sc.key_of_block(b) : 0ull;
     }
     tk.cnt = R * 32;
-    tk.cta_flush(bufs, scratch, NW, lane, warp);
+    tk.cta_bootstrap(bufs, NW, R, lane, warp);
   }
+  TPQ_PHASE(1);
   sc.run(b_begin + warp + R * NW, b_end);
-  tk.cta_flush(bufs, scratch, NW, lane, warp);                 // drain every warp's staging buffer with one CTA-wide sort
+  TPQ_PHASE(2);
+  tk.flush(lane);                                              // leftovers: sorted in registers, merged under the lock
+  __syncthreads();
+  TPQ_PHASE(3);
+#ifdef TPQ_DEBUG_KNOBS
+  if (A.phase && tid == 0) atomicAdd(A.phase + 4, 1ull);
+#endif
   uint64_t* out = A.keys_out + ((size_t)q * A.S + slice) * A.k;
   for (int i = tid; i < A.k; i += NW * 32) out[i] = tk.list[i];
 }
@@ -477,6 +509,10 @@ static int g_prof_n = 0;
 static cudaEvent_t g_prof_start[kProfMax], g_prof_stop[kProfMax];
 static bool g_prof_created = false;
 
+#ifdef TPQ_DEBUG_KNOBS
+static unsigned long long* g_phase = nullptr;     // device buffer set by tpq_debug_set_phase_buffer (debug build only)
+#endif
+
 static int pick_slices(const tpq_index* ix, int nq, int k) {
   // enough CTAs for ~2 waves of 2 CTAs/SM when the batch is small
   (void)k;
@@ -487,13 +523,16 @@ static int pick_slices(const tpq_index* ix, int nq, int k) {
   return s > 64 ? 64 : s;
 }
 
-// LUT source: built inside the scan CTA when d/M is small (the codebook slice a CTA must read, M*dsub KB,
-// is then no bigger than a couple of LUTs), staged through HBM otherwise.  TPQ_LUT_MODE=staged|fused overrides.
+// LUT source: built inside the scan CTA when d/M is 1, 2, 4 or 8 (the codebook slice a CTA reads from L2, M*dsub KB,
+// is then small next to the codes it goes on to stream: C4, d/M = 8, reads 0.98 MB of codebook per 7.5 MB of codes and
+// saves the 2 x 128 KB LUT round trip through HBM plus one launch); staged through HBM by lut_scan_kernel otherwise.
 static int fused_dsub(const tpq_index* ix) {
   const int dsub = ix->d_vector / ix->n_subvectors;
+#ifdef TPQ_DEBUG_KNOBS
   const char* mode = getenv("TPQ_LUT_MODE");
   if (mode && !strcmp(mode, "staged")) return 0;
-  return (dsub == 1 || dsub == 2 || dsub == 4) ? dsub : 0;
+#endif
+  return (dsub == 1 || dsub == 2 || dsub == 4 || dsub == 8) ? dsub : 0;
 }
 
 struct SearchWs {
@@ -544,7 +583,11 @@ static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cel
     A.codes = ix->codes_scan; A.valid = ix->block_valid; A.cell_block_start = ix->cell_block_start;
     A.cell_start = ix->cell_start; A.lut_scan = lut_ws; A.cells = cells; A.n_probe_list = npl; A.keys_out = keys;
     A.nq = nq; A.q_base = q0; A.n_probe = n_probe; A.k = k; A.kp = kp; A.S = S;
-    { const char* br = getenv("TPQ_BOOT_R"); A.boot_r = br ? atoi(br) : 2; if (A.boot_r < 1 || A.boot_r > 2) A.boot_r = 2; }
+    A.boot_r = 2; A.n_cells = ix->n_cells;
+#ifdef TPQ_DEBUG_KNOBS
+    { const char* br = getenv("TPQ_BOOT_R"); if (br && atoi(br) == 1) A.boot_r = 1; }
+    A.phase = g_phase;
+#endif
     const bool prof = g_prof_on && g_prof_n < kProfMax;
     if (prof) cudaEventRecord(g_prof_start[g_prof_n], st);
     kern<<<n * S, NW * 32, L.total, st>>>(A, L);
@@ -562,6 +605,7 @@ static int launch_scan(const tpq_index* ix, const float* x, const int64_t* cells
     case 1:  return launch_scan_d<MP, NW, MINB, 1>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
     case 2:  return launch_scan_d<MP, NW, MINB, 2>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
     case 4:  return launch_scan_d<MP, NW, MINB, 4>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+    case 8:  return launch_scan_d<MP, NW, MINB, 8>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
     default: return launch_scan_d<MP, NW, MINB, 0>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
   }
 }
@@ -600,6 +644,7 @@ static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cel
 #undef TPQ_RES
   }
 #define TPQ_SCAN_ARGS ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st
+#ifdef TPQ_DEBUG_KNOBS
   // tuning knob for experiments (scripts/sweep_scan.py): TPQ_SCAN_CFG = "<warps>x<min CTAs/SM>"
   const char* cfg = getenv("TPQ_SCAN_CFG");
   if (cfg && ix->m_pad == 64) {
@@ -608,6 +653,7 @@ static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cel
     if (!strcmp(cfg, "16x1")) return launch_scan<64, 16, 1>(TPQ_SCAN_ARGS);
     if (!strcmp(cfg, "4x4"))  return launch_scan<64, 4, 4>(TPQ_SCAN_ARGS);
   }
+#endif
   switch (ix->m_pad) {
     case 32:  return launch_scan<32, 8, 2>(TPQ_SCAN_ARGS);
     case 64: {
@@ -630,6 +676,10 @@ static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cel
 }  // namespace tpq
 
 using namespace tpq;
+
+#ifdef TPQ_DEBUG_KNOBS
+extern "C" int tpq_debug_set_phase_buffer(unsigned long long* dev_buf8) { g_phase = dev_buf8; return TPQ_OK; }
+#endif
 
 extern "C" int tpq_profile_enable(int on) {
   if (on && !g_prof_created) {

@@ -6,8 +6,8 @@ and ``search`` / ``search_cells`` signatures and return values as the reference 
 container/BaseContainer.py:32-38).  All computation is the sm_100a library behind
 ``include/tpq_b200.h``; PyTorch is used for device memory and streams only.
 
-Not covered (out of the hot-path scope): residual PQ
-(``pq_use_residual=True``), ``use_cublas=False`` / tensor-core coarse variants.
+Residual IVFPQ (``pq_use_residual=True``) runs the RES variant of the scan kernel.  Not covered (out of the
+hot-path scope): ``use_cublas=False`` / tensor-core coarse variants (flags accepted, ignored).
 """
 from __future__ import annotations
 
@@ -19,6 +19,14 @@ import torch
 from . import _lib
 from ._lib import lib, check, ptr
 from .modules import StateModule, Codec
+
+
+def _codebook_of(codec):
+    """The codec's centroid buffer without going through ``is_trained`` (a device->host read in the reference's
+    BaseCodec): torchpq_b200 codecs and torchpq codecs both keep it at ``codec.kmeans.centroids``."""
+    km = getattr(codec, "kmeans", None)
+    cb = getattr(km, "centroids", None) if km is not None else None
+    return cb if cb is not None else codec.codebook
 
 
 def _fingerprint(*tensors):
@@ -80,6 +88,9 @@ class ScanLayout:
         check(lib.tpq_relayout_codebook(ptr(index.pq_codec.codebook), d, M, ix.metric,
                                         ptr(self.pq_codebook_t), ptr(self.pq_norm_t), stream))
         self.fingerprint = _fingerprint(*self.keep)
+        self.stream_id = (stream.value or 0)                                  # searches on another stream wait on `ready`
+        self.ready = torch.cuda.Event()
+        self.ready.record(torch.cuda.current_stream(dev))
 
 
 class IVFPQIndex(StateModule):
@@ -146,6 +157,18 @@ class IVFPQIndex(StateModule):
     def _state_changed(self):
         self._layout = None
 
+    def load_state_dict(self, state_dict, strict=True):
+        """Reference semantics (CustomModule.py:14-23) + the one piece of state the reference keeps outside its
+        buffers: ``_max_id`` (BaseContainer.py:30,49-51) is re-derived from ``_address2id`` so that ids handed out
+        after a load do not restart at 0 and ``get_address_by_id`` sizes its inverse map correctly."""
+        super().load_state_dict(state_dict, strict)
+        self._refresh_max_id()
+
+    def _refresh_max_id(self):
+        a2i = self._address2id
+        self._max_id = int(a2i.max().item()) if a2i is not None and a2i.numel() else -1
+        self._id2address_fp = None
+
     # ------------------------------------------------------------------ state import
     def load_state(self, st):
         """Adopt an ``oracle.ivfpq_oracle.IndexState``-shaped object (numpy buffers) -- test/bench helper."""
@@ -178,12 +201,16 @@ class IVFPQIndex(StateModule):
             self._layout = None
 
     def layout(self) -> ScanLayout:
-        fp = _fingerprint(self._storage, self._is_empty, self._cell_start, self._cell_size, self._address2id,
-                          self.vq_codec.codebook, self.pq_codec.codebook)
+        vq, pq = _codebook_of(self.vq_codec), _codebook_of(self.pq_codec)     # no host sync (is_trained.item()) per search
+        fp = _fingerprint(self._storage, self._is_empty, self._cell_start, self._cell_size, self._address2id, vq, pq)
         if self._layout is None or self._layout.fingerprint != fp:
             assert self.vq_codec.is_trained and self.pq_codec.is_trained, "codec is not trained"
             self._layout = ScanLayout(self, *self._shard)
-        return self._layout
+        lay = self._layout
+        cur = torch.cuda.current_stream(self._storage.device)
+        if lay.ready is not None and cur.cuda_stream != lay.stream_id:
+            cur.wait_event(lay.ready)                                  # layout kernels ran on another stream
+        return lay
 
     # ------------------------------------------------------------------ search
     def _check_query(self, x, k):
@@ -269,6 +296,8 @@ class IVFPQIndex(StateModule):
         if self._id2address is None or self._id2address_fp != _fingerprint(self._address2id):
             a2i_v, a2i_i = self._address2id.sort()
             keep = a2i_v >= 0
+            if a2i_v.numel():                                          # never trust a stale _max_id (checkpoint loads)
+                self._max_id = max(self._max_id, int(a2i_v[-1].item()))
             id2a = -torch.ones(self._max_id + 1, dtype=torch.long, device=ids.device)
             id2a[a2i_v[keep]] = a2i_i[keep]
             delattr(self, "_id2address")

@@ -54,7 +54,12 @@ class Codec(StateModule):
 
     @property
     def is_trained(self) -> bool:
-        return bool(self._is_trained.item())
+        # cached as a Python bool: `.item()` on a CUDA `_is_trained` would be a host sync on every search
+        t = self._is_trained
+        key = (t.data_ptr(), t._version)
+        if getattr(self, "_trained_key", None) != key:
+            self._trained_cache, self._trained_key = bool(t.item()), key
+        return self._trained_cache
 
     @property
     def codebook(self):
