@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """Headline benchmark: queries/sec at recall@100 of IVFPQ search (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|tiny]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|c3c|tiny]
 
 A "step" is one ``IVFPQIndex.search`` call over one batch of ``--nq`` synthetic queries.
 Default workload = BASELINE.json configs[2] (the config the metric is quoted on):
 10M x 128 fp32 randn base, M=64, n_cells=4096, n_probe=32, k=100, index cell-sharded over N GPUs.
-Prints ONE JSON line on rank 0 (see the task's bench contract for the fields).
+Prints ONE JSON line on rank 0 (see the task's bench contract for the fields).  At N=1 with the default workload
+the line carries a ``secondary`` block: the same measurement on configs 2 and 4, on a clustered variant of config 3
+(meaningful recall, smart probing actually pruning), the C5 k-means kernels, the build side, and the reference's own
+``ivfpq_topk`` GPU kernel (compiled unmodified for sm_100a into oracle/_ref) timed on the same index and queries.
 
 --impl reference: the reference has no CPU path and cannot be imported without CuPy + a GPU
 (torchpq/__init__.py:2-5), so the reference arm times the repo's CPU restatement of it
@@ -16,6 +19,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -33,30 +37,70 @@ WORKLOADS = {
     "c3":   (10_000_000, 128, 64, 4096, 32, 100, "euclidean", 1 << 20, "10Mx128 fp32 randn, M=64, n_cells=4096, nprobe=32, k=100"),
     "c2":   (1_000_000, 128, 64, 1024, 32, 100, "euclidean", 1 << 18, "1Mx128 fp32 randn, M=64, n_cells=1024, nprobe=32, k=100"),
     "c4":   (1_000_000, 960, 120, 1024, 64, 100, "cosine", 1 << 17, "1Mx960 fp32 randn (GIST-shaped), M=120, n_cells=1024, nprobe=64, cosine, k=100"),
+    "c3c":  (10_000_000, 128, 64, 4096, 32, 100, "euclidean", 1 << 20, "10Mx128 fp32 clustered (256 Gaussian centres + unit noise), M=64, n_cells=4096, nprobe=32, k=100"),
     "tiny": (100_000, 128, 64, 256, 16, 100, "euclidean", 1 << 16, "100kx128 smoke workload"),
 }
+CLUSTERED = {"c3c"}
+VQ_ITERS, PQ_ITERS = 15, 25          # the reference's training lengths (IVFPQIndex.py:63-71, PQCodec.py:27-32)
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def host_threads():
+    """CPU threads this process may actually use: the affinity mask capped by the cgroup cpu quota
+    (os.cpu_count() ignores both and made the round-1 CPU baseline swing 8x between boxes)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                      # cgroup v2: "<quota> <period>" or "max <period>"
+            q, p = f.read().split()[:2]
+            if q != "max":
+                quota = float(q) / float(p)
+    except (OSError, ValueError):
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except (OSError, ValueError):
+            pass
+    if quota:
+        n = max(1, min(n, int(math.floor(quota + 1e-9)) or 1))
+    return n, {"affinity": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
+               "os_cpu_count": os.cpu_count(), "cgroup_quota_cpus": quota}
+
+
 # ----------------------------------------------------------------------------- synthetic index (setup, not timed)
-def gen_base(d, n, device, seed=1234, chunk=1 << 20):
+def cluster_centres(d, n_cells, device, seed=99):
+    """4 * sqrt(C) Gaussian centres (unit-variance coordinates); points = centre + unit noise."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    return torch.randn(d, 4 * int(round(math.sqrt(n_cells))), generator=g, device=device)
+
+
+def gen_base(d, n, device, seed=1234, chunk=1 << 20, centres=None):
     g = torch.Generator(device=device).manual_seed(seed)
     x = torch.empty(d, n, dtype=torch.float32, device=device)
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
         x[:, s:e] = torch.randn(d, e - s, generator=g, device=device)
+        if centres is not None:
+            pick = torch.randint(0, centres.shape[1], (e - s,), generator=g, device=device)
+            x[:, s:e] += centres[:, pick]
     return x
 
 
-def build_index(wl, device, vq_iters=4, pq_iters=4):
-    """Train + add with the torch-op build side (torchpq_b200/build.py); returns (index, base)."""
+def build_index(wl, device, vq_iters=VQ_ITERS, pq_iters=PQ_ITERS, clustered=False):
+    """Train + add with the library's build side (torchpq_b200/build.py); returns (index, base)."""
     import torchpq_b200 as T
     from torchpq_b200 import build
     N, d, M, C, n_probe, k, distance, n_train, _ = wl
-    base = gen_base(d, N, device)
+    centres = cluster_centres(d, C, device) if clustered else None
+    base = gen_base(d, N, device, centres=centres)
     tmp = T.IVFPQIndex(d, M, C, initial_size=1, distance=distance, device=str(device))
     build.train(tmp, base[:, :n_train].contiguous(), seed=0, vq_iters=vq_iters, pq_iters=pq_iters)
     cells_l, codes_l = [], []
@@ -76,13 +120,14 @@ def build_index(wl, device, vq_iters=4, pq_iters=4):
     return index, base
 
 
-def build_state_torch(wl, device, vq_iters=4, pq_iters=4):
+def build_state_torch(wl, device, vq_iters=VQ_ITERS, pq_iters=PQ_ITERS, clustered=False):
     """Reference arm only: the same synthetic index built with plain torch ops (no torchpq_b200 code at all) and
-    returned as an oracle IndexState.  Seeded Lloyd with matmul arg-max assignment, placement = stable sort by cell
-    (what CellContainer.add does for one add into a fresh container, CellContainer.py:334-353)."""
+    returned as an oracle IndexState.  Seeded Lloyd with matmul arg-max assignment and the reference's stopping rule
+    (sum of squared centroid shifts <= 1e-4), placement = stable sort by cell (what CellContainer.add does for one add
+    into a fresh container, CellContainer.py:334-353)."""
     from oracle import ivfpq_oracle as O
     N, d, M, C, n_probe, k, distance, n_train, _ = wl
-    base = gen_base(d, N, device)
+    base = gen_base(d, N, device, centres=cluster_centres(d, C, device) if clustered else None)
     if distance == "cosine":
         base = base / (base.norm(dim=0, keepdim=True) + 1e-9)
 
@@ -105,7 +150,11 @@ def build_state_torch(wl, device, vq_iters=4, pq_iters=4):
             lab = assign(data, cent)
             sums = torch.zeros(l, dd, kk, device=device).scatter_add_(2, lab[:, None, :].expand(l, dd, n), data)
             cnt = torch.zeros(l, kk, device=device).scatter_add_(1, lab, ones)
-            cent = torch.where(cnt[:, None, :] > 0, sums / cnt.clamp(min=1)[:, None, :], torch.zeros((), device=device))
+            new = torch.where(cnt[:, None, :] > 0, sums / cnt.clamp(min=1)[:, None, :], torch.zeros((), device=device))
+            err = float((new - cent).pow(2).sum())
+            cent = new
+            if err <= 1e-4:
+                break
         return cent
 
     tr = base[:, :n_train].contiguous()
@@ -137,16 +186,21 @@ def build_state_torch(wl, device, vq_iters=4, pq_iters=4):
                         max_id=N - 1, n_probe=n_probe)
 
 
-def gen_queries(d, nq, n_batches, device, seed=4321):
+def gen_queries(d, nq, n_batches, device, seed=4321, centres=None):
     g = torch.Generator(device="cpu").manual_seed(seed)
-    return [torch.randn(d, nq, generator=g).pin_memory() if device.type == "cuda" else torch.randn(d, nq, generator=g)
-            for _ in range(n_batches)]
+    out = []
+    for _ in range(n_batches):
+        x = torch.randn(d, nq, generator=g)
+        if centres is not None:
+            c = centres.cpu()
+            x = x + c[:, torch.randint(0, c.shape[1], (nq,), generator=g)]
+        out.append(x.pin_memory() if device.type == "cuda" else x)
+    return out
 
 
 def exact_truth(base, x, k, distance, chunk=1 << 20):
     """Exact top-k ids of x [d, nq] in base by brute force fp32 (ids = column index = add order)."""
     if distance == "cosine":
-        base_n = None
         x = x / (x.norm(dim=0, keepdim=True) + 1e-9)
     best_v = torch.full((x.shape[1], k), -float("inf"), device=x.device)
     best_i = torch.zeros((x.shape[1], k), dtype=torch.long, device=x.device)
@@ -184,7 +238,7 @@ def to_oracle_state(index):
 
 
 def oracle_search(st, x, k, threads):
-    """oracle.search with the scan done by the OpenMP C restatement (same semantics, all host threads)."""
+    """oracle.search with the scan done by the OpenMP C restatement (same semantics, all usable host threads)."""
     from oracle import ivfpq_oracle as O, c_oracle as CO
     xx, sims, cells, npl = O.coarse_probe(st, x)
     lut = O.precompute_adc(xx, torch.from_numpy(st.pq_codebook), st.distance).numpy()
@@ -200,6 +254,22 @@ def time_oracle(st, xs, k, threads, target_s=12.0):
     n2 = int(min(xs.shape[1], max(n, n * target_s / max(dt, 1e-3))))
     t0 = time.perf_counter(); _, _, used = oracle_search(st, xs[:, :n2].contiguous(), k, threads); dt = time.perf_counter() - t0
     return n2 / dt, n2, used
+
+
+def parity_vs_oracle(st, x_host, v_ours, ids_ours, truth, k, threads, n):
+    """ours vs the CPU oracle on the first n queries: id sets, values (rtol 1e-3), recall of both."""
+    ov, oi, _ = oracle_search(st, x_host[:, :n].contiguous(), k, threads)
+    v, ids = v_ours[:n].cpu().numpy(), ids_ours[:n].cpu().numpy()
+    same_sets = float((np.sort(ids, 1) == np.sort(oi, 1)).all(axis=1).mean())
+    fin = np.isfinite(ov)
+    rel = np.abs(v[fin] - ov[fin]) / np.maximum(np.abs(ov[fin]), 1e-6)
+    out = {"n_queries": n, "rows_with_identical_id_sets": same_sets, "id_overlap": float(np.mean([
+               np.intersect1d(ids[q], oi[q]).shape[0] / float(k) for q in range(n)])),
+           "values_max_rel_err": float(rel.max(initial=0.0)), "values_within_1e-3": bool(rel.max(initial=0.0) <= 1e-3)}
+    if truth is not None:
+        out["recall_at_100_oracle"] = recall(torch.from_numpy(oi), truth[:n])
+        out["recall_at_100_ours"] = recall(torch.from_numpy(ids), truth[:n])
+    return out
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -249,6 +319,203 @@ class ClockSampler:
         return out
 
 
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        try:
+            return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- device measurements on one index
+def cuda_time(fn, steps, warmup=3, device=None):
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record(); torch.cuda.synchronize(device)
+    return e0.elapsed_time(e1) / steps
+
+
+def scan_roofline(index, xs_dev, k, reps, rank=0, shards=1, query_slice=None):
+    """Roofline of the scan kernel on this rank: algorithmic bytes / CUDA-event duration of the scan launches
+    (tpq_profile_* brackets every scan launch with events on its own stream).
+    B_q = M * sum_{j < P_q} cell_size[cells[q, j]] over the cells this rank owns + 12 k  (SURVEY.md section 8d)."""
+    import ctypes
+    import torchpq_b200 as T
+    lib = T._lib.lib
+    n_probe, M = int(index.n_probe), index.n_subvectors
+    dev = xs_dev[0].device
+    sel = (lambda x: x) if query_slice is None else (lambda x: x[:, query_slice[0]:query_slice[1]].contiguous())
+    lib.tpq_profile_enable(1)
+    torch.cuda.synchronize(dev)
+    for i in range(reps):
+        index.search(sel(xs_dev[i % len(xs_dev)]), k=k)
+    ms_scan, n_launch = ctypes.c_float(0), ctypes.c_int(0)
+    T._lib.check(lib.tpq_profile_scan_ms(ctypes.byref(ms_scan), ctypes.byref(n_launch)))
+    lib.tpq_profile_enable(0)
+    alg_bytes, probes = 0, 0.0
+    for i in range(reps):
+        x = sel(xs_dev[i % len(xs_dev)])
+        if index.distance == "cosine":
+            x = T.fn.normalize(x)
+        _, cells, npl = T.fn.coarse_probe(x, index.vq_codec.codebook, n_probe, index.use_smart_probing,
+                                          index.smart_probing_temperature)
+        P = npl.clamp(1, n_probe)
+        sizes = index._cell_size[cells]
+        owned = (cells % shards) == rank
+        mask = (torch.arange(n_probe, device=dev)[None, :] < P[:, None]) & owned
+        alg_bytes += int((sizes * mask).sum().item()) * M + 12 * k * x.shape[1]
+        probes += float(P.float().mean().item())
+    n = max(1, n_launch.value)
+    ms = ms_scan.value / n
+    return {"scan_ms_per_launch": ms, "algorithmic_bytes_per_launch": alg_bytes / n,
+            "achieved_gbs": (alg_bytes / n) / (ms / 1e3) / 1e9 if n_launch.value else None,
+            "mean_probes_scanned": probes / reps, "launches": n_launch.value}
+
+
+def profiled_traffic(workload, world):
+    """dram bytes per scan launch from an ncu --set full capture of THIS workload at N=1 (profiles/scan_traffic.json);
+    null anywhere it was not profiled."""
+    if world != 1:
+        return None
+    tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    try:
+        return json.load(open(tp)).get(workload)
+    except Exception:
+        return None
+
+
+def measure_single_gpu(name, index, base, device, nq, steps, threads, with_oracle_parity=True, centres=None):
+    """Device-timed QPS + scan roofline + recall on one workload (secondary block)."""
+    N, d, M, C, n_probe, k, distance, n_train, desc = WORKLOADS[name]
+    xs_host = gen_queries(d, nq, 4, device, centres=centres)
+    xs_dev = [x.to(device) for x in xs_host]
+    ms = cuda_time(lambda i: index.search(xs_dev[i % 4], k=k), steps, device=device)
+    rf = scan_roofline(index, xs_dev, k, min(steps, 4))
+    peak, _ = hbm_peak()
+    nr = min(1000, nq)
+    xr = xs_dev[0][:, :nr].contiguous()
+    truth = exact_truth(base, xr, k, distance)
+    v_r, ids_r = index.search(xr, k=k)
+    out = {"workload": f"{name}: {desc}", "n_query_per_step": nq, "queries_per_s": nq / ms * 1e3, "ms_per_step": ms,
+           "recall_at_100": recall(ids_r, truth), "use_smart_probing": bool(index.use_smart_probing),
+           "mean_probes_scanned": rf["mean_probes_scanned"],
+           "roofline": {"kernel": "ivfpq_scan_kernel", "achieved": rf["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                        "frac": rf["achieved_gbs"] / peak if rf["achieved_gbs"] else None,
+                        "algorithmic_bytes_per_launch": rf["algorithmic_bytes_per_launch"],
+                        "scan_ms_per_launch": rf["scan_ms_per_launch"], "scan_share_of_step": rf["scan_ms_per_launch"] / ms,
+                        "step_frac_of_peak": rf["algorithmic_bytes_per_launch"] / (ms / 1e3) / 1e9 / peak}}
+    if with_oracle_parity:
+        try:
+            st = to_oracle_state(index)
+            out["vs_oracle"] = parity_vs_oracle(st, xs_host[0], v_r, ids_r, truth, k, threads, nr)
+        except Exception as e:
+            out["vs_oracle"] = {"error": repr(e)}
+    return out
+
+
+def reference_gpu_kernel(index, xs_dev, k, steps=3):
+    """The reference's own `ivfpq_topk` kernel (kernels/cuda/ivfpq_topk.cu:822-971, compiled unmodified for sm_100a
+    with its own launch parameters into oracle/_ref, tpb=256) on the SAME index state and queries, fed the LUT and the
+    gathered cell tables the reference's host code would feed it.  SURVEY section 2b's bar: beat this kernel."""
+    try:
+        from oracle import ref_kernels as R
+        import torchpq_b200 as T
+        M = index.n_subvectors
+        if not R.available(M):
+            return {"unavailable": f"oracle/_ref has no ivfpq_topk build for M={M}"}
+        if index.capacity > (1 << 24):
+            return {"unavailable": "capacity above 2^24: the reference kernel carries addresses in a float"}
+        x = xs_dev[0]
+        xq = T.fn.normalize(x) if index.distance == "cosine" else x
+        _, cells, npl = T.fn.coarse_probe(xq, index.vq_codec.codebook, int(index.n_probe), index.use_smart_probing,
+                                          index.smart_probing_temperature)
+        lut = T.fn.precompute_adc(xq, index.pq_codec.codebook, index.distance)
+        cs, cz = index._cell_start[cells].contiguous(), index._cell_size[cells].contiguous()
+        run = lambda i: R.ivfpq_topk(index._storage, lut, cs, cz, index._is_empty, npl, k)
+        ms = cuda_time(run, steps, warmup=1, device=x.device)
+        P = npl.clamp(1, int(index.n_probe))
+        mask = torch.arange(cells.shape[1], device=x.device)[None, :] < P[:, None]
+        byts = int((cz * mask).sum().item()) * M + 12 * k * x.shape[1]
+        rv, ra = run(0)
+        v, _, a = index.search(x, k=k, return_address=True)
+        agree = float(torch.isclose(rv, v, rtol=1e-4, atol=0).all(dim=1).float().mean().item())
+        peak, _ = hbm_peak()
+        return {"kernel": "torchpq ivfpq_topk (tpb=256), compiled for sm_100a from /root/reference sources", "ms_per_launch": ms,
+                "queries_per_s_scan_only": x.shape[1] / ms * 1e3, "scan_gbs": byts / (ms / 1e3) / 1e9,
+                "frac_of_hbm_peak": byts / (ms / 1e3) / 1e9 / peak, "rows_with_values_equal_to_ours_rtol_1e-4": agree,
+                "note": "scan kernel only (LUT, coarse probe and gathers prepared outside the timed region)"}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
+def secondary_block(device, threads, c3_index, c3_xs_dev, k3, steps):
+    """C2 / C4 / clustered-C3 search lines, C5 k-means kernels, build side, reference GPU kernel (N=1 only)."""
+    import torchpq_b200 as T
+    from torchpq_b200 import build
+    sec = {}
+    peak, _ = hbm_peak()
+    t0 = time.time()
+    sec["reference_gpu_kernel_c3"] = reference_gpu_kernel(c3_index, c3_xs_dev, k3)
+    for name in ("c2", "c4", "c3c"):
+        try:
+            clustered = name in CLUSTERED
+            wl = WORKLOADS[name]
+            index, base = build_index(wl, device, clustered=clustered)
+            centres = cluster_centres(wl[1], wl[3], device) if clustered else None
+            sec[name] = measure_single_gpu(name, index, base, device, 10000, steps, threads, centres=centres)
+            if name == "c3c":
+                sec[name]["note"] = "queries drawn from the same Gaussian mixture as the base: recall is meaningful and smart probing prunes"
+            del index, base
+            torch.cuda.empty_cache()
+        except Exception as e:
+            sec[name] = {"error": repr(e)}
+    # ---- C5: MultiKMeans assignment + centroid update (BASELINE config 5)
+    try:
+        l, d, n, kk = 64, 64, 1_000_000, 256
+        data = torch.randn(l, d, n, device=device)
+        cent = data[:, :, :kk].contiguous()
+        byts = 4 * l * d * n + 4 * l * d * kk + 12 * l * n
+        ms = cuda_time(lambda i: T.fn.max_sim(data, cent, exact=False, exact_values=False), 3, warmup=1, device=device)
+        sec["c5_assign"] = {"kernel": "assign_tc_kernel (tcgen05 TF32)", "ms": ms, "gbs": byts / ms / 1e6,
+                            "frac_of_hbm_peak": byts / ms / 1e6 / peak, "tflops_gemm_form": 2.0 * l * n * d * kk / ms / 1e9}
+        lab = T.fn.max_sim(data, cent, exact=False, exact_values=False)[1]
+        byts_c = 4 * l * d * n + 8 * l * n + 4 * l * d * kk
+        ms = cuda_time(lambda i: T.fn.compute_centroids(data, lab, kk), 3, warmup=1, device=device)
+        sec["c5_compute_centroids"] = {"ms": ms, "gbs": byts_c / ms / 1e6, "frac_of_hbm_peak": byts_c / ms / 1e6 / peak}
+        del data, lab
+        torch.cuda.empty_cache()
+    except Exception as e:
+        sec["c5"] = {"error": repr(e)}
+    # ---- build side: add 1M vectors (encode + place) into a fresh index with the C3 codebooks
+    try:
+        wl = WORKLOADS["c3"]
+        xb = gen_base(wl[1], 1_000_000, device, seed=77)
+        ix2 = T.IVFPQIndex(wl[1], wl[2], wl[3], initial_size=512, device=str(device))
+        ix2.vq_codec.set_codebook(c3_index.vq_codec.codebook); ix2.pq_codec.set_codebook(c3_index.pq_codec.codebook)
+        build.encode(ix2, xb[:, :1 << 16].contiguous())
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        cells, codes = build.encode(ix2, xb)
+        torch.cuda.synchronize(); t_enc = time.perf_counter() - t1
+        t1 = time.perf_counter()
+        build.container_add(ix2, codes, cells)
+        torch.cuda.synchronize(); t_place = time.perf_counter() - t1
+        sec["add_1M"] = {"encode_s": t_enc, "place_s": t_place, "vectors_per_s": 1e6 / (t_enc + t_place),
+                         "encode_input_gbs": xb.numel() * 4 / t_enc / 1e9}
+        del xb, ix2
+        torch.cuda.empty_cache()
+    except Exception as e:
+        sec["add_1M"] = {"error": repr(e)}
+    sec["seconds"] = time.time() - t0
+    return sec
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -260,24 +527,37 @@ def main():
     ap.add_argument("--nq", type=int, default=10000)
     ap.add_argument("--no-smart", action="store_true", help="use_smart_probing=False (fixed work per query)")
     ap.add_argument("--cpu-sample", type=float, default=12.0, help="seconds of CPU-oracle work for cpu_baseline")
+    ap.add_argument("--query-groups", type=int, default=0,
+                    help="multi-GPU grid: ranks = cell_shards x query_groups (0 = auto: 1 up to 4 GPUs, 2 at 8)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary block (c2/c4/c3c/C5/build/reference kernel)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
+    clustered = args.workload in CLUSTERED
     N, d, M, C, n_probe, k, distance, n_train, desc = wl
     have_cuda = torch.cuda.is_available()
     device = torch.device(f"cuda:{local_rank}" if have_cuda else "cpu")
     if have_cuda:
         torch.cuda.set_device(device)
-    threads = os.cpu_count() or 1
+    threads, thread_info = host_threads()
     torch.set_num_threads(threads)
+    groups = args.query_groups if args.query_groups > 0 else (2 if world >= 8 else 1)
+    if world % groups:
+        groups = 1
+    shards = world // groups
+    config = {"workload": f"{args.workload}: {desc}", "n_query_per_step": args.nq,
+              "index_sharding": f"cells mod {shards}" + (f" x {groups} query groups" if groups > 1 else ""),
+              "use_smart_probing": not args.no_smart,
+              "l2_policy": "inputs larger than L2 (code store >= 640 MB vs 126 MB L2; 4 rotating query batches)",
+              "training": f"seeded k-means, <= {VQ_ITERS} (coarse) / {PQ_ITERS} (PQ) Lloyd iterations, tol 1e-4 (the reference's settings)"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        return run_reference(args, wl, device, threads)
+        return run_reference(args, wl, device, threads, thread_info, config, clustered)
 
     assert have_cuda, "bench.py --impl ours needs a CUDA device (no CPU fallback)"
     import torch.distributed as dist
@@ -286,30 +566,55 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     assert T._lib.lib.tpq_device_supported(local_rank), "libtpq_b200.so is built for sm_100a"
-
-    t0 = time.time()
-    if rank == 0:
-        index, base = build_index(wl, device)
-    else:
-        index, base = T.IVFPQIndex(d, M, C, initial_size=1, distance=distance, device=str(device)), None
-        index.n_probe = n_probe
-    if world > 1:
-        tdist.broadcast_state(index, 0)
-    index.use_smart_probing = not args.no_smart
-    index.set_shard(rank, world)
-    lay = index.layout()
-    torch.cuda.synchronize()
-    log(f"[rank {rank}] index built in {time.time() - t0:.1f}s: capacity={index.capacity} blocks={lay.n_blocks}")
+    grid = (shards, groups)
+    coarse_group = None
+    if world > 1 and groups > 1:
+        for g in range(groups):                                       # every rank creates every group, keeps its own
+            pg = dist.new_group(list(range(g * shards, (g + 1) * shards)))
+            if rank // shards == g:
+                coarse_group = pg
 
     nq = args.nq
-    xs_host = gen_queries(d, nq, 4, device)
+    centres = cluster_centres(d, C, device) if clustered else None
+    xs_host = gen_queries(d, nq, 4, device, centres=centres)
     xs_dev = [x.to(device) for x in xs_host]
 
-    def step_device(i):
-        x = xs_dev[i % len(xs_dev)]
+    t0 = time.time()
+    st_cpu, truth, unsharded0, full_bytes = None, None, None, None
+    nr = min(1000, nq)
+    if rank == 0:
+        index, base = build_index(wl, device, clustered=clustered)
+        index.use_smart_probing = not args.no_smart
+        # everything that needs the FULL index happens here, before the index is cut into shards
+        truth = exact_truth(base, xs_dev[0][:, :nr].contiguous(), k, distance)
+        del base
+        torch.cuda.empty_cache()
+        index.layout()
+        full_bytes = index.resident_bytes()                            # reference buffers + scan layout of all cells
         if world > 1:
-            return tdist.sharded_search(index, x, k)
+            unsharded0 = index.search(xs_dev[0], k=k)
+        try:
+            st_cpu = to_oracle_state(index)
+        except Exception as e:
+            log(f"oracle state export failed: {e!r}")
+    else:
+        index = T.IVFPQIndex(d, M, C, initial_size=1, distance=distance, device=str(device))
+        index.n_probe = n_probe
+    index.use_smart_probing = not args.no_smart
+    if world > 1:
+        tdist.distribute(index, 0, grid=grid)
+    lay = index.layout()
+    torch.cuda.synchronize()
+    resident = index.resident_bytes()
+    log(f"[rank {rank}] index ready in {time.time() - t0:.1f}s: capacity={index.capacity} blocks={lay.n_blocks} resident={resident / 1e6:.0f} MB")
+
+    def search(x):
+        if world > 1:
+            return tdist.sharded_search(index, x, k, grid=grid, coarse_group=coarse_group)
         return index.search(x, k=k)
+
+    def step_device(i):
+        return search(xs_dev[i % len(xs_dev)])
 
     # end-to-end leg: host (pinned) queries in, host (pinned) results out, every step.  Copies run on their own
     # stream with double-buffered staging tensors, so step i's D2H and step i+1's H2D overlap step i+1's search --
@@ -331,10 +636,7 @@ def main():
             x_in[b].copy_(xs_host[i % len(xs_host)], non_blocking=True)
             ev_in[b].record(copy_stream)
         main.wait_event(ev_in[b])
-        if world > 1:
-            v, ids = tdist.sharded_search(index, x_in[b], k)
-        else:
-            v, ids = index.search(x_in[b], k=k)
+        v, ids = search(x_in[b])
         ev_free[b].record(main)
         ev_done[b].record(main)
         res[b] = (v, ids)                                            # keep alive until the copy stream has read them
@@ -371,119 +673,97 @@ def main():
     qps = nq * args.steps / (ms_dev / 1e3)
     qps_e2e = nq * args.steps / (ms_e2e / 1e3)
 
-    # ---- roofline of the scan kernel: algorithmic bytes / CUDA-event duration of the scan launches
-    T._lib.lib.tpq_profile_enable(1)
+    # ---- roofline of the scan kernel on this rank (its own query group, its own cells)
     barrier()
-    reps = min(args.steps, 5)
-    for i in range(reps):
-        index.search(xs_dev[i % len(xs_dev)], k=k)
-    import ctypes
-    ms_scan, n_launch = ctypes.c_float(0), ctypes.c_int(0)
-    T._lib.check(T._lib.lib.tpq_profile_scan_ms(ctypes.byref(ms_scan), ctypes.byref(n_launch)))
-    T._lib.lib.tpq_profile_enable(0)
-    alg_bytes = 0
-    for i in range(reps):                                    # B_q = M * sum_{j<P_q} cell_size[cells[q,j]] + 12 k
-        x = xs_dev[i % len(xs_dev)]
-        _, cells, npl = T.fn.coarse_probe(x, index.vq_codec.codebook, n_probe, index.use_smart_probing,
-                                          index.smart_probing_temperature)
-        P = npl.clamp(1, n_probe)
-        sizes = index._cell_size[cells]
-        owned = (cells % world) == rank
-        mask = (torch.arange(n_probe, device=device)[None, :] < P[:, None]) & owned
-        alg_bytes += int((sizes * mask).sum().item()) * M + 12 * k * nq
-    scan_ms_per_launch = ms_scan.value / max(1, n_launch.value)
-    achieved = alg_bytes / max(1, n_launch.value) / (scan_ms_per_launch / 1e3) / 1e9 if n_launch.value else None
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get(args.workload)
-        except Exception:
-            traffic = None
+    per_group = (nq + groups - 1) // groups
+    qsl = None if groups == 1 else (min(nq, (rank // shards) * per_group), min(nq, (rank // shards + 1) * per_group))
+    rf = scan_roofline(index, xs_dev, k, min(args.steps, 5), rank=rank % shards, shards=shards, query_slice=qsl)
+    peak, peak_src = hbm_peak()
 
-    # sharded run: does the cell-sharded search (all ranks, NCCL) return exactly what the unsharded index returns?
-    sharded_ok = None
+    # per-rank resident bytes (max over ranks) -- "shard the index" means memory per rank falls with the shard count
+    res_t = torch.tensor([float(resident)], device=device)
     if world > 1:
-        try:
-            v_s, i_s = tdist.sharded_search(index, xs_dev[0], k)
-            torch.cuda.synchronize()
-            if rank == 0:
-                index.set_shard(0, 1)
-                v_u, i_u = index.search(xs_dev[0], k=k)
-                sharded_ok = bool(torch.equal(v_s, v_u) and torch.equal(i_s, i_u))
-                index.set_shard(rank, world)
-        except Exception as e:                                       # report, never take the number down
-            sharded_ok = f"check failed: {e!r}"
+        dist.all_reduce(res_t, op=dist.ReduceOp.MAX)
+
+    # sharded run: does the cell-sharded search (all ranks, NCCL) return exactly what the unsharded index returned?
+    sharded_ok = None
+    v_r = ids_r = None
+    try:
+        v_s, i_s = search(xs_dev[0])
+        torch.cuda.synchronize()
+        v_r, ids_r = v_s[:nr], i_s[:nr]
+        if world > 1 and rank == 0:
+            sharded_ok = bool(torch.equal(v_s, unsharded0[0]) and torch.equal(i_s, unsharded0[1]))
+    except Exception as e:                                           # report, never take the number down
+        sharded_ok = f"check failed: {e!r}"
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
 
-    # ---- recall@100 (ours vs exact brute force) on 1000 queries; oracle on its CPU sample
-    nr = min(1000, nq)
-    xr = xs_dev[0][:, :nr].contiguous()
-    truth = exact_truth(base, xr, k, distance)
-    if world > 1:
-        index.set_shard(0, 1)                                # full index on rank 0 for the recall / parity leg
-    v_r, ids_r = index.search(xr, k=k)
-    rec = recall(ids_r, truth)
-
+    # ---- recall@100 (ours vs exact brute force) on 1000 queries; CPU oracle: timing sample + parity on the same 1000
+    rec = recall(ids_r, truth) if ids_r is not None else None
     cpu = None
     try:
-        st = to_oracle_state(index)
-        qps_cpu, n_cpu, used = time_oracle(st, xs_host[0].clone(), k, threads, args.cpu_sample)
-        nv = min(n_cpu, nr, 128)
-        ov, oi, _ = oracle_search(st, xs_host[0][:, :nv].contiguous(), k, threads)
-        rec_oracle = recall(torch.from_numpy(oi), truth[:nv])
-        rec_ours_same = recall(ids_r[:nv], truth[:nv])
-        same = float((np.sort(ids_r[:nv].cpu().numpy(), 1) == np.sort(oi, 1)).all(axis=1).mean())
-        cpu = {"value": qps_cpu, "unit": "queries/s", "cores": used, "kind": "port",
+        qps_cpu, n_cpu, used = time_oracle(st_cpu, xs_host[0].clone(), k, threads, args.cpu_sample)
+        par = parity_vs_oracle(st_cpu, xs_host[0], v_r, ids_r, truth, k, threads, nr)
+        cpu = {"value": qps_cpu, "unit": "queries/s", "cores": used, "kind": "port", "threads_source": thread_info,
                "sample": f"{n_cpu} of the {nq} queries of batch 0, full {args.workload} index, oracle (torch-CPU matmul + OpenMP C scan)",
-               "recall_at_100": rec_oracle, "recall_at_100_ours_same_queries": rec_ours_same,
-               "rows_with_identical_id_sets": same}
+               "recall_at_100": par.get("recall_at_100_oracle"), "recall_at_100_ours_same_queries": par.get("recall_at_100_ours"),
+               "parity_queries": par["n_queries"], "rows_with_identical_id_sets": par["rows_with_identical_id_sets"],
+               "id_overlap": par["id_overlap"], "values_max_rel_err": par["values_max_rel_err"],
+               "values_within_1e-3": par["values_within_1e-3"]}
     except Exception as e:  # the CPU leg must not take the GPU number down with it
         cpu = {"value": None, "error": repr(e)}
+    st_cpu = None
+
+    secondary = None
+    if world == 1 and args.workload == "c3" and not args.no_secondary:
+        try:
+            secondary = secondary_block(device, threads, index, xs_dev, k, min(args.steps, 10))
+        except Exception as e:
+            secondary = {"error": repr(e)}
 
     # our kernels per search: 2 x col_sqnorm, coarse_gemm, probe_select, ivfpq_scan, merge_topk
-    # (+ normalize_columns for cosine, + lut_scan when d/M is not 1/2/4, + the cross-shard merge when sharded)
-    launches_per_step = 6 + (1 if distance == "cosine" else 0) + (0 if (d // M) in (1, 2, 4) else 1) + (1 if world > 1 else 0)
+    # (+ normalize_columns for cosine, + lut_scan when d/M is not 1/2/4/8, + the cross-shard merge(s) when sharded)
+    launches_per_step = 6 + (1 if distance == "cosine" else 0) + (0 if (d // M) in (1, 2, 4, 8) else 1) + (groups if world > 1 else 0)
+    ach = rf["achieved_gbs"]
     line = {
         "metric": "queries/sec @ recall@100, IVFPQ search", "value": qps, "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 codes / fp32 LUT+accumulate",
-        "data": "synthetic (randn base seed 1234, randn queries seed 4321; codebooks trained on-device by seeded k-means)",
-        "config": {"workload": f"{args.workload}: {desc}", "n_query_per_step": nq, "index_sharding": f"cells mod {world}",
-                   "use_smart_probing": index.use_smart_probing,
-                   "l2_policy": "inputs larger than L2 (code store >= 640 MB vs 126 MB L2; 4 rotating query batches)"},
+        "data": "synthetic (" + ("Gaussian-mixture" if clustered else "randn") + " base seed 1234, queries seed 4321; codebooks trained on-device by seeded k-means)",
+        "config": config,
         "recall_at_100": rec, "sharded_equals_unsharded": sharded_ok,
+        "resident_bytes_per_rank_max": res_t.item(), "resident_bytes_full_index_one_gpu": full_bytes,
         "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": d * nq * 4, "d2h_bytes_per_step": nq * k * 12,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"kernel": "ivfpq_scan_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes / max(1, n_launch.value),
-                     "scan_ms_per_launch": scan_ms_per_launch, "scan_share_of_step": scan_ms_per_launch / (ms_dev / args.steps)},
-        "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": {"kernel": "ivfpq_scan_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": (ach / peak) if ach else None, "traffic": profiled_traffic(args.workload, world), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": rf["algorithmic_bytes_per_launch"],
+                     "scan_ms_per_launch": rf["scan_ms_per_launch"],
+                     "scan_share_of_step": rf["scan_ms_per_launch"] / (ms_dev / args.steps),
+                     "mean_probes_scanned": rf["mean_probes_scanned"], "rank": 0},
+        "cpu_baseline": cpu, "clocks": clocks, "secondary": secondary,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
-def run_reference(args, wl, device, threads):
+def run_reference(args, wl, device, threads, thread_info, config, clustered):
     """CPU arm: the oracle restatement on the host cores; each step = a bounded query sample."""
     N, d, M, C, n_probe, k, distance, n_train, desc = wl
-    st = build_state_torch(wl, device)            # plain torch ops only; nothing of torchpq_b200 is imported on this arm
+    st = build_state_torch(wl, device, clustered=clustered)   # plain torch ops only; nothing of torchpq_b200 is imported on this arm
     st.use_smart_probing = not args.no_smart
     if device.type == "cuda":
         torch.cuda.empty_cache()
-    xs = gen_queries(d, args.nq, 1, torch.device("cpu"))[0]
+    centres = cluster_centres(d, C, torch.device("cpu")) if clustered else None
+    xs = gen_queries(d, args.nq, 1, torch.device("cpu"), centres=centres)[0]
     # size the per-step sample so that (steps + warmup) fit in about two minutes
     qps0, n0, used = time_oracle(st, xs, k, threads, target_s=3.0)
     per_step = int(max(16, min(args.nq, qps0 * 120.0 / max(1, args.steps + args.warmup))))
@@ -499,10 +779,11 @@ def run_reference(args, wl, device, threads):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 codes / fp32 LUT+accumulate",
         "data": "synthetic (same generator as the GPU arm)",
-        "config": {"workload": f"{args.workload}: {desc}", "n_query_per_step": per_step,
-                   "use_smart_probing": st.use_smart_probing},
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": used, "kind": "port",
-                         "sample": f"{per_step} queries per step against the full {args.workload} index (reference has no CPU path; oracle restatement)"},
+        "config": config,
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": used, "kind": "port", "threads_source": thread_info,
+                         "sample": f"{per_step} of the {args.nq} queries per step against the full {args.workload} index "
+                                   "(reference has no CPU path; oracle restatement: torch-CPU matmuls + OpenMP C scan)",
+                         "sample_queries_per_step": per_step},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)

@@ -121,7 +121,7 @@ def test_churn_keeps_capacity_bounded(cuda_device):
     for cycle in range(6):
         gone = ids[cycle::2][:1500]
         ix.remove(ids=gone)
-        ids_new = ix.add(base[:, :gone.shape[0]].contiguous())       # different vectors land in different cells
+        ids_new = ix.add(torch.randn(32, gone.shape[0], device="cuda"))   # fresh vectors land in different cells
         ids = torch.cat([ids[~torch.isin(ids, gone)], ids_new])
         assert ix.n_items == 4000
         assert (ix._cell_size <= ix._cell_capacity).all()

@@ -166,3 +166,49 @@ def test_sharded_search_plumbing_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 2-D grid: world 4 = 2 cell shards x 2 query groups (dist.make_grid), split coarse probe inside each query group
+# ---------------------------------------------------------------------------------------------------------------
+def worker_grid(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import ivfpq_oracle as O, build_state as B
+    from torchpq_b200 import dist as tdist
+    tdist.fn.coarse_probe = _cpu_coarse_probe
+    tdist.fn.merge_topk = _cpu_merge
+    st, queries = B.integer_state(32, 8, 16, 3000, seed=7)
+    st.n_probe, st.use_smart_probing = 6, True
+    x, k = queries(23), 9                                 # 23 queries over 2 groups: 12 + 11 (padded), then 6 + 6 per rank
+    fv, fi, fa = O.search(st, x, k=k, return_address=True)
+    ok = True
+    for groups in (2, 1, 4):
+        grid = tdist.make_grid(world, groups)
+        shards = grid[0]
+        cgs = [dist.new_group(list(range(g * shards, (g + 1) * shards))) for g in range(groups)]
+        ix = _OracleIndex(st, rank % shards, shards)
+
+        def search(xx, k=1, return_keys=False, _ix=ix):   # replicated coarse probe (used when shards == 1)
+            s, c, npl = _cpu_coarse_probe(xx, _ix.vq_codec.codebook, _ix.n_probe, True, 30.0)
+            return _ix.search_cells(xx, c, base_sims=s, n_probe_list=npl, k=k, return_keys=True)
+        ix.search = search
+        v, ids, a = tdist.sharded_search(ix, x, k, return_address=True, grid=grid, coarse_group=cgs[rank // shards])
+        ok = ok and np.array_equal(v.numpy(), fv) and np.array_equal(a.numpy(), fa) and np.array_equal(ids.numpy(), fi)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_grid_sharded_search_gloo():
+    world = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=worker_grid, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]

@@ -32,6 +32,19 @@ def _worker(rank, world, port, q):
     for split in (True, False):
         v, i, a = tdist.sharded_search(ix, x, 25, return_address=True, split_coarse=split)
         ok = ok and torch.equal(v, v0) and torch.equal(i, i0) and torch.equal(a, a0)
+    # shard-only ranks (dist.distribute): rank 0 owns the full index, every rank ends up with its cells' scan layout
+    # only (no _storage / _is_empty anywhere), for both grids a 2-rank world allows
+    for grid in ((2, 1), (1, 2)):
+        full = T.IVFPQIndex(64, 16, 32, initial_size=1, device=f"cuda:{rank}")
+        if rank == 0:
+            full.load_state(st)
+        tdist.distribute(full, 0, grid=grid)
+        ok = ok and full._storage is None and full._is_empty is None
+        v, i, a = tdist.sharded_search(full, x, 25, return_address=True, grid=grid, split_coarse=False)
+        ok = ok and torch.equal(v, v0) and torch.equal(i, i0) and torch.equal(a, a0)
+        if grid == (2, 1):
+            lay = full.layout()
+            ok = ok and lay.n_blocks < ix.layout().n_blocks + 64 and full.resident_bytes() > 0
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

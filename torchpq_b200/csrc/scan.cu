@@ -148,6 +148,7 @@ struct Scanner {
   static constexpr int NSB = Units<MP>::NSB;
   const uint8_t* codes; const uint32_t* valid; const uint8_t* lut;
   const int32_t* seg_prefix; const int32_t* seg_blk0; const uint32_t* seg_addr0;
+  int* next;                                            // CTA-wide cursor: next block (of the concatenated probe list) to hand out
   int lane;
   uint32_t off[8];
   uint32_t regs[2][16];
@@ -205,29 +206,39 @@ struct Scanner {
     const float score = base + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
     return ((v >> lane) & 1u) ? make_key(score, a0 + lane) : 0ull;
   }
-  __device__ __forceinline__ void run(int b, int b_end) {
+  // Blocks are handed out dynamically: `next` is a CTA-wide counter in shared memory.  (A static stripe b = warp,
+  // warp + NW, ... left the CTA waiting for its slowest warp -- the warp schedulers favour the oldest warps, so the
+  // youngest ones finished 5 % (C3) to 30 % (C4, 16 warps, one CTA per SM) later than warp 0.)  The index of the
+  // block after next is fetched before the current block is consumed, so the atomic's latency is off the critical path.
+  __device__ __forceinline__ int grab() {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(next, 1);
+    return __shfl_sync(0xffffffffu, b, 0);
+  }
+  __device__ __forceinline__ void run(int b_end) {
+    int b = grab();
     if (b >= b_end) return;
     locate(b, B_cur, a0_cur);
     load_unit<MP, 0>(regs[0], codes, B_cur, lane);
     valid_cur = __ldg(valid + B_cur);
     for (;;) {
-      bool more = b + NW < b_end;
-      if (more) locate(b + NW, B_nxt, a0_nxt);
+      b = grab();
+      bool more = b < b_end;
+      if (more) locate(b, B_nxt, a0_nxt);
       process_block<0>(more);
       if (!more) break;
-      b += NW;
       if constexpr (NSB % 2 == 1) {                       // odd unit count: the buffers swap roles every block
-        more = b + NW < b_end;
-        if (more) locate(b + NW, B_nxt, a0_nxt);
+        b = grab();
+        more = b < b_end;
+        if (more) locate(b, B_nxt, a0_nxt);
         process_block<1>(more);
         if (!more) break;
-        b += NW;
       }
     }
   }
 };
 
-struct ScanSmem { size_t lut, part1, seg_blk0, seg_addr0, seg_cell, seg_prefix, thr, lock, list, bufs, total; };
+struct ScanSmem { size_t lut, part1, seg_blk0, seg_addr0, seg_cell, seg_prefix, thr, lock, rep, list, bufs, total; };
 static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp, bool residual = false) {
   ScanSmem s; size_t off = 0;
   s.lut = off;        off += (size_t)((MP + 63) / 64) * 65536;
@@ -238,9 +249,10 @@ static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp, bool residual = f
   s.seg_prefix = off; off += (size_t)(n_probe + 1) * 4;
   off = align_up(off, 8);
   s.thr = off;        off += 8;
-  s.lock = off;       off += 8;
+  s.lock = off;       off += 16;                                      // list lock, drain counter, block cursor
+  s.rep = off;        off += (size_t)nw * 8;
   s.list = off;       off += (size_t)kp * 8;
-  s.bufs = off;       off += (size_t)nw * kTopkBuf * 8;
+  s.bufs = off;       off += (size_t)nw * kStage * 8;
   s.total = off;
   return s;
 }
@@ -261,6 +273,7 @@ struct ScanArgs {
   int n_cells;                    // probe entries outside [0, n_cells) are treated as empty segments
 #ifdef TPQ_DEBUG_KNOBS
   unsigned long long* phase;      // [8] summed clock64 deltas: prologue, bootstrap, scan, drain; [4] = CTAs
+  int boot_mode;                  // 1 = merge-tree bootstrap (A/B against the quick start)
 #endif
 };
 
@@ -283,6 +296,9 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   const int qi = blockIdx.x / A.S, slice = blockIdx.x % A.S;  // query within this chunk
   const int q = A.q_base + qi;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef TPQ_DEBUG_KNOBS
+  long long t_ph = clock64();
+#endif
 
   // --- probe segments first (warp 0): their dependent global loads overlap the other warps' LUT work (same visiting rules as scan_ref.cu / ivfpq_topk.cu:837-870)
   int P = (int)A.n_probe_list[q];
@@ -369,7 +385,6 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
     }
   }
 #ifdef TPQ_DEBUG_KNOBS
-  long long t_ph = clock64();
   auto phase_mark = [&](int i) {
     if (A.phase && tid == 0) { const long long t = clock64(); atomicAdd(A.phase + i, (unsigned long long)(t - t_ph)); t_ph = t; }
   };
@@ -380,8 +395,9 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   Scanner<MP, NW> sc;
   sc.codes = A.codes; sc.valid = A.valid; sc.lut = lut;
   sc.seg_prefix = seg_prefix; sc.seg_blk0 = seg_blk0; sc.seg_addr0 = seg_addr0; sc.lane = lane;
+  sc.next = reinterpret_cast<int*>(smem + L.lock) + 2;
   sc.tk.init(reinterpret_cast<uint64_t*>(smem + L.list), reinterpret_cast<unsigned long long*>(smem + L.thr),
-             reinterpret_cast<int*>(smem + L.lock), reinterpret_cast<uint64_t*>(smem + L.bufs) + (size_t)warp * kTopkBuf,
+             reinterpret_cast<int*>(smem + L.lock), reinterpret_cast<uint64_t*>(smem + L.bufs) + (size_t)warp * kStage,
              A.kp, A.k);
   // lane's slot offsets: byte r%4 of off[r/4] = ((lane + r) & 31) * 4
   #pragma unroll
@@ -408,6 +424,7 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       const int b0 = seg_prefix[j], b1 = seg_prefix[j + 1];
       if (b1 == b0) continue;                                          // skipped entry, empty cell or another shard's cell
       __syncthreads();                                                 // every warp is done with the previous cell's LUT
+      if (tid == 0) *sc.next = b0;
       const float4* p2 = reinterpret_cast<const float4*>(A.part2_scan + (size_t)seg_cell[j] * MG * 16384);
       #pragma unroll 4
       for (int i = tid; i < MG * 4096; i += NW * 32) {                 // store_precomputed_to_smem: part1 + part2 (:609-628)
@@ -416,10 +433,9 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       }
       __syncthreads();
       sc.base = A.base_sims[(size_t)q * A.n_probe + j];
-      sc.run(b0 + warp, b1);
+      sc.run(b1);
     }
-    tk.flush(lane);
-    __syncthreads();
+    tk.cta_drain(bufs, lane, warp);
     uint64_t* outr = A.keys_out + (size_t)q * A.k;
     for (int i = tid; i < A.k; i += NW * 32) outr[i] = tk.list[i];
     return;
@@ -428,6 +444,7 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   // log2(NW)-level merge tree, which establishes the threshold (k-th best of the first R * NW * 32 vectors) without
   // R * NW lock-serialised flushes.
   const int R = A.boot_r;
+  if (tid == 0) *sc.next = b_begin + R * NW;                    // the bootstrap's barriers publish it
   {
     #pragma unroll 1
     for (int r = 0; r < R; ++r) {
@@ -435,13 +452,15 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       tk.buf[r * 32 + lane] = (b < b_end) ? sc.key_of_block(b) : 0ull;
     }
     tk.cnt = R * 32;
-    tk.cta_bootstrap(bufs, NW, R, lane, warp);
+#ifdef TPQ_DEBUG_KNOBS
+    if (A.boot_mode == 1) tk.cta_bootstrap(bufs, NW, R, lane, warp); else
+#endif
+    tk.cta_quickstart(reinterpret_cast<uint64_t*>(smem + L.rep), NW, R, lane, warp);
   }
   TPQ_PHASE(1);
-  sc.run(b_begin + warp + R * NW, b_end);
+  sc.run(b_end);
   TPQ_PHASE(2);
-  tk.flush(lane);                                              // leftovers: sorted in registers, merged under the lock
-  __syncthreads();
+  tk.cta_drain(bufs, lane, warp);                          // leftovers of all warps: register sorts + merge tree, no lock
   TPQ_PHASE(3);
 #ifdef TPQ_DEBUG_KNOBS
   if (A.phase && tid == 0) atomicAdd(A.phase + 4, 1ull);
@@ -587,6 +606,7 @@ static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cel
 #ifdef TPQ_DEBUG_KNOBS
     { const char* br = getenv("TPQ_BOOT_R"); if (br && atoi(br) == 1) A.boot_r = 1; }
     A.phase = g_phase;
+    { const char* bm = getenv("TPQ_BOOT_MODE"); A.boot_mode = bm ? atoi(bm) : 0; }
 #endif
     const bool prof = g_prof_on && g_prof_n < kProfMax;
     if (prof) cudaEventRecord(g_prof_start[g_prof_n], st);

@@ -31,7 +31,7 @@ static RefScanSmem ref_scan_smem(int M, int n_probe, int nw, int kp) {
   s.thr = off;        off += 8;
   s.lock = off;       off += 8;
   s.list = off;       off += (size_t)kp * sizeof(uint64_t);
-  s.bufs = off;       off += (size_t)nw * kTopkBuf * sizeof(uint64_t);
+  s.bufs = off;       off += (size_t)nw * kStage * sizeof(uint64_t);
   s.total = off;
   return s;
 }
@@ -92,7 +92,7 @@ ivfpq_topk_ref_kernel(const uint32_t* __restrict__ data,        // [M/4, n_data]
   }
   CtaTopK tk;
   tk.init(reinterpret_cast<uint64_t*>(smem + L.list), reinterpret_cast<unsigned long long*>(smem + L.thr),
-          reinterpret_cast<int*>(smem + L.lock), reinterpret_cast<uint64_t*>(smem + L.bufs) + (size_t)warp * kTopkBuf,
+          reinterpret_cast<int*>(smem + L.lock), reinterpret_cast<uint64_t*>(smem + L.bufs) + (size_t)warp * kStage,
           kp, k);
   __syncthreads();
 
@@ -121,7 +121,7 @@ ivfpq_topk_ref_kernel(const uint32_t* __restrict__ data,        // [M/4, n_data]
     const uint64_t key = make_key(score, (uint32_t)a);
     tk.push(live && key > tk.threshold(), key, lane);
   }
-  tk.flush(lane);
+  tk.flush(lane, true);
   __syncthreads();
   // write-out: descending, (-inf, -1) padded  (ivfpq_topk.cu:966-970; IVFPQTopkCuda.py:118-120,142)
   for (int i = tid; i < k; i += blockDim.x) {

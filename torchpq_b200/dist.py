@@ -1,13 +1,18 @@
-"""Cell-sharded multi-GPU search: one process per GPU, one NCCL all-gather per query batch.
+"""Cell-sharded multi-GPU search: one process per GPU, one NCCL all-gather of candidates per query batch.
 
 The reference is single-GPU only (no NCCL / torch.distributed anywhere).
-Partitioning: rank r scans the cells c with c % world == r; the two small
-codebooks and the address->id table are replicated; every rank sees the full query batch, runs
-the (deterministic, identical) coarse probe redundantly, scans only its own cells and emits its
-local top-k as packed 64-bit (score, address) keys.  One ``all_gather_into_tensor`` of
-[nq, k] keys (8 B per candidate) follows, then the same merge kernel that combines CTA slices
-picks the global top-k -- the union of per-shard top-k's contains the global top-k, and keys
-carry GLOBAL addresses, so sharded == unsharded bit for bit, ties included.
+Partitioning: the ``world`` ranks form a grid of ``cell_shards x query_groups``
+(default ``world x 1``, the north-star's pure cell sharding).  Rank r owns the cells c with
+``c % cell_shards == r % cell_shards`` and serves the queries of group ``r // cell_shards``.  Each rank holds
+only ITS cells' codes (in scan layout); the two small codebooks, the per-cell tables and the address->id table
+are replicated.  A rank runs the (deterministic) coarse probe, scans its own cells and emits its local top-k
+as packed 64-bit (score, address) keys.  ONE ``all_gather_into_tensor`` of [nq / query_groups, k] keys
+(8 B per candidate) follows, then the merge kernel picks the global top-k -- the union of per-shard top-k's
+contains the global top-k, and keys carry GLOBAL addresses, so sharded == unsharded bit for bit, ties included.
+
+``query_groups > 1`` trades memory for fixed cost: every (query, rank) pair pays one LUT build and one top-k
+bootstrap whatever the shard holds, so at 8 GPUs a 4 x 2 grid halves that replicated work (each rank then
+holds 1/4 of the codes instead of 1/8).
 """
 from __future__ import annotations
 
@@ -28,24 +33,44 @@ def _gather_rows(t: torch.Tensor, world: int, group):
     return out
 
 
+def make_grid(world: int, query_groups: int = 1):
+    """(cell_shards, query_groups) with cell_shards * query_groups == world."""
+    assert query_groups >= 1 and world % query_groups == 0, f"query_groups={query_groups} must divide world={world}"
+    return world // query_groups, query_groups
+
+
 def sharded_search(index, x: torch.Tensor, k: int, group=None, return_address: bool = False,
-                   split_coarse: bool = True):
-    """``index`` holds the full reference state on every rank and has been given its shard with
-    ``index.set_shard(rank, world)``.  Returns the same (values, ids[, address]) on every rank.
+                   split_coarse: bool = True, grid=None, coarse_group=None):
+    """``index`` holds this rank's shard (``dist.distribute``; or the full reference state with
+    ``index.set_shard(rank % cell_shards, cell_shards)``).  Returns the same (values, ids[, address]) for the whole
+    batch on every rank.
 
     split_coarse (default): the coarse probe -- the one stage that does not shrink with the shard -- is itself split
-    by QUERIES: rank r probes queries [r*nq/world, (r+1)*nq/world) and a small all-gather (n_probe+1 int64 per query)
-    hands every rank the full probe lists.  Same deterministic kernel on every rank, so the lists are bit-identical
-    to the replicated computation.  split_coarse=False runs the whole coarse probe on every rank (one collective
-    per batch in total instead of two)."""
+    by QUERIES among the ranks that share a query group: each probes 1/cell_shards of the group's queries and a small
+    all-gather (2 n_probe + 1 int64 per query) hands every rank of the group the full probe lists.  Same deterministic
+    kernel on every rank, so the lists are bit-identical to the replicated computation.  split_coarse=False runs the
+    group's whole coarse probe on every rank: exactly one collective per batch.  ``coarse_group`` = the process group
+    of this rank's query group (needed for split_coarse when query_groups > 1; ``dist.new_group`` per group)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    if world > 1 and split_coarse:
-        nq, n_probe = x.shape[1], int(index.n_probe)
-        xq = fn.normalize(x.contiguous()) if index.distance == "cosine" else x.contiguous()   # IVFPQIndex.py:474-475
-        per = (nq + world - 1) // world
-        lo = min(nq, rank * per)
-        hi = min(nq, lo + per)
+    shards, groups = grid if grid is not None else (world, 1)
+    assert shards * groups == world
+    crank, qg = rank % shards, rank // shards
+    nq_all = x.shape[1]
+    per_group = (nq_all + groups - 1) // groups
+    g_lo = min(nq_all, qg * per_group)
+    g_hi = min(nq_all, g_lo + per_group)
+    xg = x if groups == 1 else x[:, g_lo:g_hi].contiguous()
+    nq, n_probe = xg.shape[1], int(index.n_probe)
+    if groups > 1 and nq < per_group:                                  # ragged last group: pad so every rank gathers equal rows
+        xg = torch.cat([xg, xg.new_zeros(xg.shape[0], per_group - nq)], 1)
+    if shards > 1 and split_coarse and (groups == 1 or coarse_group is not None):
+        cg = group if groups == 1 else coarse_group
+        xq = fn.normalize(xg.contiguous()) if index.distance == "cosine" else xg.contiguous()   # IVFPQIndex.py:474-475
+        nqg = xq.shape[1]
+        per = (nqg + shards - 1) // shards
+        lo = min(nqg, crank * per)
+        hi = min(nqg, lo + per)
         mine = torch.zeros(per, 2 * n_probe + 1, dtype=torch.long, device=x.device)
         if hi > lo:
             sims, cells, npl = fn.coarse_probe(xq[:, lo:hi].contiguous(), index.vq_codec.codebook, n_probe,
@@ -53,24 +78,101 @@ def sharded_search(index, x: torch.Tensor, k: int, group=None, return_address: b
             mine[:hi - lo, :n_probe] = cells
             mine[:hi - lo, n_probe] = npl
             mine[:hi - lo, n_probe + 1:] = sims.view(torch.int32).to(torch.long)      # fp32 bits, exact round trip
-        allp = _gather_rows(mine, world, group)[:nq]
+        allp = _gather_rows(mine, shards, cg)[:nqg]
         base = allp[:, n_probe + 1:].to(torch.int32).view(torch.float32).contiguous()
         keys = index.search_cells(xq, allp[:, :n_probe].contiguous(), base_sims=base,
                                   n_probe_list=allp[:, n_probe].contiguous(), k=k, return_keys=True)[2]
     else:
-        _, _, keys = index.search(x, k=k, return_keys=True)
+        keys = index.search(xg, k=k, return_keys=True)[2]
     if world == 1:
         keys_all = keys[None]
     else:
         keys_all = torch.empty((world * keys.shape[0], keys.shape[1]), dtype=keys.dtype, device=keys.device)
-        dist.all_gather_into_tensor(keys_all, keys, group=group)
+        dist.all_gather_into_tensor(keys_all, keys, group=group)      # THE collective of the path: 8 B per candidate
         keys_all = keys_all.view(world, keys.shape[0], keys.shape[1])
-    values, ids, address = merge_gathered(keys_all, index._address2id)
+    if groups == 1:
+        values, ids, address = merge_gathered(keys_all, index._address2id)
+    else:                                                              # rows [g*shards, (g+1)*shards) are query group g's parts
+        outs = [merge_gathered(keys_all[g * shards:(g + 1) * shards], index._address2id) for g in range(groups)]
+        values, ids, address = (torch.cat([o[j] for o in outs], 0)[:nq_all] for j in range(3))
     return (values, ids, address) if return_address else (values, ids)
 
 
+def _bcast_tensor(t, shape, dtype, dev, src, group, rank):
+    if rank != src:
+        t = torch.empty(shape, dtype=dtype, device=dev)
+    dist.broadcast(t, src=src, group=group)
+    return t
+
+
+def distribute(index, src: int = 0, group=None, grid=None):
+    """Hand every rank ITS shard of rank ``src``'s index (trained + populated there, or loaded from a reference
+    checkpoint) and nothing more: the scan layout of the rank's own cells (1/cell_shards of the codes), the small
+    replicated state (codebooks, per-cell tables, address->id) -- no rank other than ``src`` ever sees the
+    reference-layout code store, and ``src`` drops it too unless ``keep_full``.  After the call ``index`` on every
+    rank is a shard-only index ready for ``sharded_search``."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    shards, groups = grid if grid is not None else (world, 1)
+    assert shards * groups == world
+    dev = torch.device(index.device)
+    small = ["_cell_start", "_cell_size", "_cell_capacity", "_address2id"]
+    meta = [None]
+    if rank == src:
+        meta[0] = {n: (tuple(getattr(index, n).shape), getattr(index, n).dtype) for n in small}
+        meta[0]["vq"] = tuple(index.vq_codec.codebook.shape)
+        meta[0]["pq"] = tuple(index.pq_codec.codebook.shape)
+        meta[0]["max_id"] = index._max_id
+        meta[0]["n_probe"] = index.n_probe
+    dist.broadcast_object_list(meta, src=src, group=group)
+    m = meta[0]
+    for n in small:
+        t = _bcast_tensor(getattr(index, n) if rank == src else None, *m[n], dev, src, group, rank)
+        if rank != src:
+            delattr(index, n)
+            index.register_buffer(n, t)
+    vq = _bcast_tensor(index.vq_codec.codebook if rank == src else None, m["vq"], torch.float32, dev, src, group, rank)
+    pq = _bcast_tensor(index.pq_codec.codebook if rank == src else None, m["pq"], torch.float32, dev, src, group, rank)
+    if rank != src:
+        index.vq_codec.set_codebook(vq)
+        index.pq_codec.set_codebook(pq)
+        index._max_id, index.n_probe = m["max_id"], m["n_probe"]
+    # one cell shard at a time: src lays it out, the ranks of that shard (one per query group) receive it
+    from .index import ScanLayout
+    mine = None
+    for c in range(shards):
+        owners = [c + shards * g for g in range(groups)]
+        sizes = [None]
+        lay = None
+        if rank == src:
+            lay = ScanLayout(index, c, shards)
+            sizes[0] = (lay.n_blocks, lay.codes_scan.numel(), lay.block_valid.numel())
+        dist.broadcast_object_list(sizes, src=src, group=group)
+        n_blocks, n_codes, n_valid = sizes[0]
+        if rank == src:
+            parts = (lay.codes_scan, lay.block_valid, lay.cell_block_start)
+            for o in owners:
+                if o != src:
+                    for t in parts:
+                        dist.send(t, dst=o, group=group)
+            if src in owners:
+                mine = parts + (n_blocks,)
+        elif rank in owners:
+            parts = (torch.empty(n_codes, dtype=torch.uint8, device=dev), torch.empty(n_valid, dtype=torch.int32, device=dev),
+                     torch.empty(index.n_cells + 1, dtype=torch.int32, device=dev))
+            for t in parts:
+                dist.recv(t, src=src, group=group)
+            mine = parts + (n_blocks,)
+        del lay
+    index.adopt_shard(rank % shards, shards, *mine)
+    if rank == src:
+        torch.cuda.empty_cache()
+    return index
+
+
 def broadcast_state(index, src: int = 0, group=None):
-    """Replicate rank ``src``'s index buffers (after train/add) to every rank."""
+    """Replicate rank ``src``'s FULL index state (reference layout included) to every rank -- for callers that want
+    every rank able to add / remove; ``distribute`` is the search-only, memory-sharded alternative."""
     rank = dist.get_rank(group)
     dev = torch.device(index.device)
     names = ["_storage", "_is_empty", "_cell_start", "_cell_size", "_cell_capacity", "_address2id"]

@@ -37,34 +37,42 @@ class ScanLayout:
     """The scan ("shadow") layout of one index (or of one shard of it) + its ``tpq_index`` struct.
 
     Built from the reference buffers by ``tpq_relayout_*``; rebuilt whenever any of those
-    buffers is replaced or modified in place (``add``, ``expand``, ``load_state_dict``...)."""
+    buffers is replaced or modified in place (``add``, ``expand``, ``load_state_dict``...).
+    ``parts`` = (codes_scan, block_valid, cell_block_start, n_blocks) adopts a shard that was laid out elsewhere
+    (dist.distribute): the index then needs no ``_storage`` / ``_is_empty`` at all."""
 
-    def __init__(self, index: "IVFPQIndex", shard_rank: int = 0, shard_world: int = 1):
-        dev = index._storage.device
+    def __init__(self, index: "IVFPQIndex", shard_rank: int = 0, shard_world: int = 1, parts=None):
+        dev = index._address2id.device
         assert dev.type == "cuda", "torchpq_b200 has no CPU path: the index must live on a CUDA device"
         stream = _lib.current_stream(dev)
         M, d, Cn = index.n_subvectors, index.d_vector, index.n_cells
         self.m_pad = (M + 31) // 32 * 32
-        self.keep = (index._storage, index._is_empty, index._cell_start, index._cell_size, index._address2id,
-                     index.vq_codec.codebook, index.pq_codec.codebook)
-        for t in self.keep:
+        self.shard = (shard_rank, shard_world)
+        vq, pq = _codebook_of(index.vq_codec), _codebook_of(index.pq_codec)
+        self.keep = (index._storage, index._is_empty, index._cell_start, index._cell_size, index._address2id, vq, pq)
+        for t in self.keep[2:] if parts is not None else self.keep:
             assert t is not None and t.is_contiguous()
-        self.cell_block_start = torch.empty(Cn + 1, dtype=torch.int32, device=dev)
-        check(lib.tpq_relayout_plan(ptr(index._cell_size), Cn, shard_rank, shard_world,
-                                    ptr(self.cell_block_start), stream))
-        self.n_blocks = int(self.cell_block_start[Cn].item())          # one host sync per (re)build
-        self.codes_scan = torch.empty(max(1, lib.tpq_codes_scan_bytes(M, self.n_blocks)), dtype=torch.uint8, device=dev)
-        self.block_valid = torch.empty(max(1, self.n_blocks), dtype=torch.int32, device=dev)
+        if parts is None:
+            self.cell_block_start = torch.empty(Cn + 1, dtype=torch.int32, device=dev)
+            check(lib.tpq_relayout_plan(ptr(index._cell_size), Cn, shard_rank, shard_world,
+                                        ptr(self.cell_block_start), stream))
+            self.n_blocks = int(self.cell_block_start[Cn].item())          # one host sync per (re)build
+            self.codes_scan = torch.empty(max(1, lib.tpq_codes_scan_bytes(M, self.n_blocks)), dtype=torch.uint8, device=dev)
+            self.block_valid = torch.empty(max(1, self.n_blocks), dtype=torch.int32, device=dev)
+        else:
+            self.codes_scan, self.block_valid, self.cell_block_start, self.n_blocks = parts
+            assert self.cell_block_start.shape[0] == Cn + 1 and self.cell_block_start.dtype == torch.int32
+            assert self.codes_scan.numel() >= lib.tpq_codes_scan_bytes(M, self.n_blocks)
         self.pq_codebook_t = torch.empty(256 * self.m_pad * (d // M), dtype=torch.float32, device=dev)
         self.pq_norm_t = torch.empty(256 * self.m_pad, dtype=torch.float32, device=dev)
         ix = _lib.TpqIndex()
         ix.d_vector, ix.n_subvectors, ix.n_cells = d, M, Cn
         ix.metric = _lib.METRIC[index.distance]
         ix.capacity = index._address2id.shape[0]
-        ix.vq_codebook = index.vq_codec.codebook.data_ptr()
-        ix.pq_codebook = index.pq_codec.codebook.data_ptr()
-        ix.storage = index._storage.data_ptr()
-        ix.is_empty = index._is_empty.data_ptr()
+        ix.vq_codebook = vq.data_ptr()
+        ix.pq_codebook = pq.data_ptr()
+        ix.storage = index._storage.data_ptr() if index._storage is not None else 0
+        ix.is_empty = index._is_empty.data_ptr() if index._is_empty is not None else 0
         ix.cell_start = index._cell_start.data_ptr()
         ix.cell_size = index._cell_size.data_ptr()
         ix.address2id = index._address2id.data_ptr()
@@ -79,18 +87,22 @@ class ScanLayout:
         if getattr(index, "pq_use_residual", False):
             # IVFPQIndex.precompute_part2 (IVFPQIndex.py:160-170), laid out like the shared-memory LUT
             self.part2_scan = torch.empty(lib.tpq_part2_scan_bytes(M, Cn) // 4, dtype=torch.float32, device=dev)
-            check(lib.tpq_relayout_part2(ptr(index.vq_codec.codebook), ptr(index.pq_codec.codebook), d, M, Cn,
-                                         ptr(self.part2_scan), stream))
+            check(lib.tpq_relayout_part2(ptr(vq), ptr(pq), d, M, Cn, ptr(self.part2_scan), stream))
             ix.part2_scan = self.part2_scan.data_ptr()
             ix.residual = 1
         self.cindex = ix
-        check(lib.tpq_relayout_codes(C.byref(ix), ptr(self.codes_scan), ptr(self.block_valid), stream))
-        check(lib.tpq_relayout_codebook(ptr(index.pq_codec.codebook), d, M, ix.metric,
-                                        ptr(self.pq_codebook_t), ptr(self.pq_norm_t), stream))
+        if parts is None:
+            check(lib.tpq_relayout_codes(C.byref(ix), ptr(self.codes_scan), ptr(self.block_valid), stream))
+        check(lib.tpq_relayout_codebook(ptr(pq), d, M, ix.metric, ptr(self.pq_codebook_t), ptr(self.pq_norm_t), stream))
         self.fingerprint = _fingerprint(*self.keep)
         self.stream_id = (stream.value or 0)                                  # searches on another stream wait on `ready`
         self.ready = torch.cuda.Event()
         self.ready.record(torch.cuda.current_stream(dev))
+
+    def resident_bytes(self) -> int:
+        """Device bytes of the scan layout (what a shard-only rank holds besides the replicated small state)."""
+        ts = (self.codes_scan, self.block_valid, self.cell_block_start, self.pq_codebook_t, self.pq_norm_t, self.part2_scan)
+        return sum(t.numel() * t.element_size() for t in ts if t is not None)
 
 
 class IVFPQIndex(StateModule):
@@ -147,6 +159,7 @@ class IVFPQIndex(StateModule):
 
     @property
     def n_items(self):
+        assert self._is_empty is not None, "shard-only index (dist.distribute) keeps no per-slot state"
         return int((self._is_empty == 0).sum().item())               # live vectors (== _cell_size.sum() until a remove)
 
     # flags the reference exposes and this path ignores (always the fused fp32 coarse kernel)
@@ -196,18 +209,35 @@ class IVFPQIndex(StateModule):
     def set_shard(self, rank: int, world: int):
         """Scan only the cells c with c % world == rank (cell-sharded multi-GPU search, dist.py)."""
         assert 0 <= rank < world
+        assert self._storage is not None or (rank, world) == self._shard, "shard-only index: the shard is fixed"
         if (rank, world) != self._shard:
             self._shard = (rank, world)
             self._layout = None
+
+    def adopt_shard(self, shard_rank, shard_world, codes_scan, block_valid, cell_block_start, n_blocks):
+        """Become a shard-only index (dist.distribute): the scan layout of this rank's cells was built elsewhere and the
+        reference-layout code store (`_storage`, `_is_empty`) is dropped.  Search works; add / remove need the full index."""
+        for name in ("_storage", "_is_empty"):
+            delattr(self, name)
+            self.register_buffer(name, None)
+        self._shard = (shard_rank, shard_world)
+        self._layout = ScanLayout(self, shard_rank, shard_world, parts=(codes_scan, block_valid, cell_block_start, n_blocks))
+        return self
+
+    def resident_bytes(self) -> int:
+        """Device bytes this index object holds (registered buffers, codebooks, scan layout)."""
+        n = sum(t.numel() * t.element_size() for t in self.buffers() if t is not None)
+        return n + (self._layout.resident_bytes() if self._layout is not None else 0)
 
     def layout(self) -> ScanLayout:
         vq, pq = _codebook_of(self.vq_codec), _codebook_of(self.pq_codec)     # no host sync (is_trained.item()) per search
         fp = _fingerprint(self._storage, self._is_empty, self._cell_start, self._cell_size, self._address2id, vq, pq)
         if self._layout is None or self._layout.fingerprint != fp:
+            assert self._storage is not None, "shard-only index: its state cannot change (re-distribute the full index)"
             assert self.vq_codec.is_trained and self.pq_codec.is_trained, "codec is not trained"
             self._layout = ScanLayout(self, *self._shard)
         lay = self._layout
-        cur = torch.cuda.current_stream(self._storage.device)
+        cur = torch.cuda.current_stream(self._address2id.device)
         if lay.ready is not None and cur.cuda_stream != lay.stream_id:
             cur.wait_event(lay.ready)                                  # layout kernels ran on another stream
         return lay
@@ -217,7 +247,7 @@ class IVFPQIndex(StateModule):
         assert len(x.shape) == 2                                          # IVFPQIndex.py:471
         assert x.shape[0] == self.d_vector                                # :472
         assert 0 < k <= 1024                                              # :473
-        assert x.dtype == torch.float32 and x.device == self._storage.device
+        assert x.dtype == torch.float32 and x.device == self._address2id.device
         return x.contiguous()
 
     def search(self, x, k=1, return_address=False, return_keys=False):
