@@ -128,71 +128,128 @@ centroid_accumulate_kernel(const float* __restrict__ data, const int64_t* __rest
     for (int j = tid; j < k; j += blockDim.x) if (cnt[j] != 0.f) atomicAdd(counts + (size_t)l * k + j, cnt[j]);
 }
 
-// Same update for k <= 1024 without one shared-memory atomic per element: the tile's points are counting-sorted
-// by label once (permutation in shared memory), then for every feature the row is staged in shared memory and each
-// warp sums whole label segments with contiguous permutation reads + a shuffle reduction; only the per-(feature,
-// cluster) partial of the tile goes to global memory.  tile = CS_T points, one CTA per (tile, l).
-constexpr int CS_T = 8192;
-__global__ void __launch_bounds__(512)
-centroid_sorted_kernel(const float* __restrict__ data, const int64_t* __restrict__ labels,
-                       int d, int n, int k, float* __restrict__ sums, float* __restrict__ counts) {
+// Streaming update for k <= 1024 (the path C5 takes): one CTA owns (l, a block of CG_E * CG_G = 16 features) for ALL
+// points, walks the points in tiles of CG_T, counting-sorts every tile by label once (shared-memory permutation), and
+// for each group of 4 features stages the 4 rows as one float4 per point; thread j then walks the segment of cluster
+// j (and j + 256, ...) with one LDS.128 gather per member and keeps the running sums of its clusters IN REGISTERS
+// across the whole point stream.  No shared-memory atomics on the data, no global atomics at all, no memset and no
+// finalize pass: the CTA knows its clusters' counts and writes sum / count itself.  (Round 1's centroid_sorted_kernel
+// issued one global atomicAdd per (tile, feature, cluster) -- 128 M at C5 -- and two barriers per feature row.)
+constexpr int CG_T = 4096, CG_E = 4, CG_G = 4;
+template <int KJ>
+__global__ void __launch_bounds__(256, 2)
+centroid_stream_kernel(const float* __restrict__ data, const int64_t* __restrict__ labels,
+                       int d, int n, int k, float* __restrict__ cent) {
   extern __shared__ __align__(16) uint8_t sm[];
-  float* xrow = reinterpret_cast<float*>(sm);                       // [CS_T]
-  uint16_t* perm = reinterpret_cast<uint16_t*>(xrow + CS_T);        // [CS_T] point (within tile) at sorted position
-  uint16_t* lab16 = perm + CS_T;                                    // [CS_T]
-  int* seg = reinterpret_cast<int*>(lab16 + CS_T);                  // [k + 1] segment starts
-  int* cur = seg + (k + 1);                                         // [k] scatter cursors / histogram
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const int l = blockIdx.y, n0 = blockIdx.x * CS_T, np = min(CS_T, n - n0);
-  for (int j = tid; j < k; j += blockDim.x) cur[j] = 0;
-  __syncthreads();
-  const int64_t* lab = labels + (size_t)l * n + n0;
-  for (int p = tid; p < np; p += blockDim.x) {
-    int j = (int)lab[p];
-    j = (j >= 0 && j < k) ? j : 0xFFFF;                              // out-of-range labels are ignored (as the reference does)
-    lab16[p] = (uint16_t)j;
-    if (j != 0xFFFF) atomicAdd(&cur[j], 1);
-  }
-  __syncthreads();
-  if (warp == 0) {                                                   // exclusive scan of the histogram
-    int carry = 0;
-    for (int j0 = 0; j0 < k; j0 += 32) {
-      const int j = j0 + lane;
-      const int c = j < k ? cur[j] : 0;
-      int incl = c;
+  float4* xs = reinterpret_cast<float4*>(sm);                       // [CG_T] 4 features of one point
+  uint16_t* perm = reinterpret_cast<uint16_t*>(xs + CG_T);          // [CG_T] point (within tile) at sorted position
+  uint16_t* lab16 = perm + CG_T;                                    // [CG_T]
+  int* seg = reinterpret_cast<int*>(lab16 + CG_T);                  // [k + 1] segment starts
+  int* cur = seg + (k + 1);                                         // [k] histogram / scatter cursors
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int l = blockIdx.y, e_base = blockIdx.x * (CG_E * CG_G);
+  float acc[KJ][CG_G][CG_E];
+  int cnt[KJ];
+  #pragma unroll
+  for (int a = 0; a < KJ; ++a) {
+    cnt[a] = 0;
+    #pragma unroll
+    for (int g = 0; g < CG_G; ++g)
       #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      if (j < k) { seg[j] = carry + incl - c; }
-      carry += __shfl_sync(0xffffffffu, incl, 31);
+      for (int e = 0; e < CG_E; ++e) acc[a][g][e] = 0.f;
+  }
+  const int64_t* lab_l = labels + (size_t)l * n;
+  constexpr int LPT = CG_T / 256;                                    // labels per thread per tile
+  int lreg[LPT];                                                     // this tile's labels, loaded one tile ahead
+  auto load_labels = [&](int n0) {
+    #pragma unroll
+    for (int u = 0; u < LPT; ++u) {
+      const int p = n0 + u * 256 + tid;
+      int j = 0xFFFF;
+      if (p < n) { const long long v = __ldcs(reinterpret_cast<const long long*>(lab_l + p)); j = (v >= 0 && v < k) ? (int)v : 0xFFFF; }
+      lreg[u] = j;                                                   // out-of-range labels are ignored (as the reference does)
     }
-    if (lane == 0) seg[k] = carry;
-  }
-  __syncthreads();
-  for (int j = tid; j < k; j += blockDim.x) {
-    const int c = cur[j];
-    if (c) atomicAdd(counts + (size_t)l * k + j, (float)c);
-    cur[j] = seg[j];
-  }
-  __syncthreads();
-  for (int p = tid; p < np; p += blockDim.x) {
-    const int j = lab16[p];
-    if (j != 0xFFFF) perm[atomicAdd(&cur[j], 1)] = (uint16_t)p;
-  }
-  __syncthreads();
-  for (int e = 0; e < d; ++e) {
-    const float* x = data + ((size_t)l * d + e) * n + n0;
-    for (int p = tid; p < np; p += blockDim.x) xrow[p] = x[p];
+  };
+  load_labels(0);
+  for (int n0 = 0; n0 < n; n0 += CG_T) {
+    const int np = min(CG_T, n - n0);
+    for (int j = tid; j < k; j += 256) cur[j] = 0;
     __syncthreads();
-    for (int j = warp; j < k; j += nw) {
-      const int s0 = seg[j], s1 = seg[j + 1];
-      if (s1 == s0) continue;
-      float acc = 0.f;
-      for (int i = s0 + lane; i < s1; i += 32) acc += xrow[perm[i]];
+    #pragma unroll
+    for (int u = 0; u < LPT; ++u) {
+      const int p = u * 256 + tid;
+      if (p < np) { lab16[p] = (uint16_t)lreg[u]; if (lreg[u] != 0xFFFF) atomicAdd(&cur[lreg[u]], 1); }
+    }
+    if (n0 + CG_T < n) load_labels(n0 + CG_T);                       // in flight while this tile is summed
+    __syncthreads();
+    if (warp == 0) {                                                 // exclusive scan of the histogram
+      int carry = 0;
+      for (int j0 = 0; j0 < k; j0 += 32) {
+        const int j = j0 + lane;
+        const int c = j < k ? cur[j] : 0;
+        int incl = c;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (j < k) seg[j] = carry + incl - c;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) seg[k] = carry;
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int a = 0; a < KJ; ++a) {
+      const int j = tid + 256 * a;
+      if (j < k) { cnt[a] += cur[j]; cur[j] = seg[j]; }
+    }
+    __syncthreads();
+    for (int p = tid; p < np; p += 256) {
+      const int j = lab16[p];
+      if (j != 0xFFFF) perm[atomicAdd(&cur[j], 1)] = (uint16_t)p;
+    }
+    // (the first staging barrier below also publishes perm)
+    #pragma unroll
+    for (int g = 0; g < CG_G; ++g) {
+      const int e0 = e_base + g * CG_E;
+      if (e0 >= d) break;                                            // CTA-uniform
+      const float* x0 = data + ((size_t)l * d + e0) * n + n0;
+      #pragma unroll 8
+      for (int p = tid; p < np; p += 256) {                          // 4 coalesced row reads -> one float4 per point
+        float4 v;
+        v.x = __ldcs(x0 + p);
+        v.y = e0 + 1 < d ? __ldcs(x0 + (size_t)n + p) : 0.f;
+        v.z = e0 + 2 < d ? __ldcs(x0 + 2 * (size_t)n + p) : 0.f;
+        v.w = e0 + 3 < d ? __ldcs(x0 + 3 * (size_t)n + p) : 0.f;
+        xs[p] = v;
+      }
+      __syncthreads();
       #pragma unroll
-      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) atomicAdd(sums + ((size_t)l * d + e) * k + j, acc);
+      for (int a = 0; a < KJ; ++a) {
+        const int j = tid + 256 * a;
+        if (j < k) {
+          const int s1 = seg[j + 1];
+          float4 t = make_float4(acc[a][g][0], acc[a][g][1], acc[a][g][2], acc[a][g][3]);
+          for (int i = seg[j]; i < s1; ++i) {
+            const float4 v = xs[perm[i]];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+          }
+          acc[a][g][0] = t.x; acc[a][g][1] = t.y; acc[a][g][2] = t.z; acc[a][g][3] = t.w;
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
+  }
+  #pragma unroll
+  for (int a = 0; a < KJ; ++a) {
+    const int j = tid + 256 * a;
+    if (j >= k) continue;
+    const float c = (float)cnt[a];
+    #pragma unroll
+    for (int g = 0; g < CG_G; ++g)
+      #pragma unroll
+      for (int e = 0; e < CG_E; ++e) {
+        const int ee = e_base + g * CG_E + e;
+        if (ee < d) cent[((size_t)l * d + ee) * k + j] = cnt[a] == 0 ? 0.f : __fdiv_rn(acc[a][g][e], c);   // compute_centroids.cu:80
+      }
   }
 }
 
@@ -272,15 +329,23 @@ extern "C" int tpq_compute_centroids(const float* data, const int64_t* labels, i
   }
   cudaStream_t st = (cudaStream_t)stream;
   float* counts = reinterpret_cast<float*>(ws);
+  if (n > 0 && k <= 1024) {
+    // streaming kernel: sums in registers, one launch, deterministic ownership of every output element
+    const size_t smem = (size_t)CG_T * 16 + (size_t)CG_T * 2 * 2 + (size_t)(2 * k + 1) * 4;
+    dim3 grid((unsigned)((d + CG_E * CG_G - 1) / (CG_E * CG_G)), l);
+#define TPQ_CSTREAM(KJ)                                                                                              \
+    do {                                                                                                             \
+      TPQ_CUDA(cudaFuncSetAttribute(centroid_stream_kernel<KJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      centroid_stream_kernel<KJ><<<grid, 256, smem, st>>>(data, labels, d, (int)n, k, centroids);                    \
+    } while (0)
+    if (k <= 256) TPQ_CSTREAM(1); else if (k <= 512) TPQ_CSTREAM(2); else TPQ_CSTREAM(4);
+#undef TPQ_CSTREAM
+    TPQ_LAUNCH_CHECK("centroid_stream_kernel");
+    return TPQ_OK;
+  }
   TPQ_CUDA(cudaMemsetAsync(centroids, 0, (size_t)l * d * k * 4, st));
   TPQ_CUDA(cudaMemsetAsync(counts, 0, (size_t)l * k * 4, st));
-  if (n > 0 && k <= 1024) {
-    const size_t smem = (size_t)CS_T * 4 + (size_t)CS_T * 2 * 2 + (size_t)(2 * k + 1) * 4;
-    TPQ_CUDA(cudaFuncSetAttribute(centroid_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((n + CS_T - 1) / CS_T), l);
-    centroid_sorted_kernel<<<grid, 512, smem, st>>>(data, labels, d, (int)n, k, centroids, counts);
-    TPQ_LAUNCH_CHECK("centroid_sorted_kernel");
-  } else if (n > 0) {
+  if (n > 0) {
     int de = (int)((160 * 1024 / 4 - k) / k);               // features per CTA so that (de+1)*k floats fit 160 KB
     if (de < 1) { set_error("tpq_compute_centroids: k=%d too large for one shared-memory row set", k); return TPQ_ERR_UNSUPPORTED; }
     if (de > d) de = d;
