@@ -109,9 +109,10 @@ int tpq_ivfpq_topk(const uint8_t* data, const float* precomputed, const uint8_t*
                    float* values, int64_t* address, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ scan layout
- * tpq_relayout_plan: cell_block_start[c] = sum_{c'<c, owned} ceil(cell_size[c']/32); [C] = total.
- * Cells not owned by (rank, world) get zero blocks.  Device->device, no sync. */
-int tpq_relayout_plan(const int64_t* cell_size, int n_cells, int shard_rank, int shard_world,
+ * tpq_relayout_plan: cell_block_start[c] = sum_{c'<c, owned} ceil(cell_extent[c']/32); [C] = total.  The caller passes
+ * the cells' CAPACITIES (blocks exist for every slot a cell can hold, so that tpq_store_codes can add items in place;
+ * the scan reads only the first ceil(cell_size/32) of them).  Cells not owned by (rank, world) get zero blocks. */
+int tpq_relayout_plan(const int64_t* cell_extent, int n_cells, int shard_rank, int shard_world,
                       int32_t* cell_block_start /* [C+1] */, void* stream);
 /* Bytes of codes_scan for n_blocks blocks of an M-subvector index. */
 size_t tpq_codes_scan_bytes(int M, int64_t n_blocks);
@@ -163,6 +164,35 @@ size_t tpq_compute_centroids_workspace_bytes(int l, int k);
 int tpq_compute_centroids(const float* data, const int64_t* labels, int l, int d, int64_t n, int k,
                           float* centroids, void* ws, size_t ws_bytes, void* stream);
 int tpq_pq_decode(const float* codebook, const uint8_t* code, int M, int dsub, int64_t n, float* out, void* stream);
+
+/* ------------------------------------------------------------------ build side: placement of new items
+ * IVFPQIndex.add -> CellContainer.add (container/CellContainer.py:313-367).
+ * tpq_get_ioa: index of appearance of every label among equal labels, input order (kernels/cuda/get_ioa.cu:8-47);
+ *   counts [n_cells] (nullable) = items per cell (what `cells.unique(return_counts=True)` feeds `_cell_size[...] +=`).
+ * tpq_empty_prefix: prefix[a] = empty slots in [0, a), a = 0..capacity (only needed when the container has holes).
+ * tpq_get_write_address: the ioa-th empty slot of the item's cell (kernels/cuda/get_write_address_v2.cu:9-41);
+ *   empty_prefix == NULL asserts "no holes": the empties of a cell are [start + size, start + capacity).  -1 = no room.
+ * tpq_store_codes: set_data_by_address (CellContainer.py:213-239) + address2id / is_empty / cell_size updates
+ *   (:354-360; cell_size becomes max(old, slot + 1)).  codes [M, n] u8.  If codes_scan / block_valid (the scan layout of
+ *   `index`, non-const here) are given they are updated in place, so the layout stays valid after the add.
+ * tpq_expand_move: CellContainer.expand (:249-311) for many cells at once: every old slot a moves to a + shift[cell(a)];
+ *   the caller pre-fills the new buffers (storage 0, address2id -1, is_empty 1) and updates the per-cell tables. */
+size_t tpq_ioa_workspace_bytes(int64_t n, int n_cells);
+int tpq_get_ioa(const int64_t* cells, int64_t n, int n_cells, int64_t* ioa, int64_t* counts,
+                void* ws, size_t ws_bytes, void* stream);
+size_t tpq_empty_prefix_workspace_bytes(int64_t capacity);
+int tpq_empty_prefix(const uint8_t* is_empty, int64_t capacity, uint32_t* prefix /* [capacity + 1] */,
+                     void* ws, size_t ws_bytes, void* stream);
+int tpq_get_write_address(const int64_t* cells, const int64_t* ioa, int64_t n,
+                          const int64_t* cell_start, const int64_t* cell_size, const int64_t* cell_capacity,
+                          int n_cells, const uint32_t* empty_prefix, int64_t* write_adr, void* stream);
+int tpq_store_codes(const uint8_t* codes, const int64_t* cells, const int64_t* write_adr, const int64_t* ids,
+                    int64_t n, tpq_index* index, uint8_t* storage, int64_t* address2id, uint8_t* is_empty,
+                    int64_t* cell_size, uint8_t* codes_scan, uint32_t* block_valid, void* stream);
+int tpq_expand_move(const uint8_t* old_storage, const int64_t* old_address2id, const uint8_t* old_is_empty,
+                    const int64_t* old_cell_start, const int64_t* shift, int n_cells, int M,
+                    int64_t old_capacity, int64_t new_capacity,
+                    uint8_t* storage, int64_t* address2id, uint8_t* is_empty, void* stream);
 
 /* ------------------------------------------------------------------ measurement hook (bench.py roofline leg)
  * When enabled, every scan-kernel launch is bracketed by CUDA events on its own stream;

@@ -111,38 +111,21 @@ def encode(index, x: torch.Tensor):
     return cells, codes
 
 
-def _ioa(cells: torch.Tensor) -> torch.Tensor:
-    """index of appearance of each label among equal labels, input order (get_ioa.cu:8-47)."""
-    n = cells.shape[0]
-    order = torch.sort(cells, stable=True).indices
-    sc = cells[order]
-    first = torch.ones(n, dtype=torch.bool, device=cells.device)
-    first[1:] = sc[1:] != sc[:-1]
-    ar = torch.arange(n, device=cells.device)
-    run_start = torch.cummax(torch.where(first, ar, torch.zeros_like(ar)), 0).values
-    ioa = torch.empty(n, dtype=torch.long, device=cells.device)
-    ioa[order] = ar - run_start
-    return ioa
-
-
-def _expand(index, cells: torch.Tensor):
-    """CellContainer.expand (CellContainer.py:249-311), one rebuild for all listed cells."""
+def _expand(index, grow: torch.Tensor):
+    """CellContainer.expand (CellContainer.py:249-311) for all cells with grow[c] > 0 in one pass: the per-cell tables
+    are [n_cells] tensor arithmetic, the slot move is the library's tpq_expand_move kernel."""
+    from ._lib import lib, check, ptr
+    from . import _lib
     dev = index._storage.device
-    grow = torch.zeros(index.n_cells, dtype=torch.long, device=dev)
-    grow[cells] = index._cell_capacity[cells] if index.expand_mode == "double" else index.expand_step_size
     shift = torch.cumsum(grow, 0) - grow                           # slots inserted before each cell
-    old_start, old_cap = index._cell_start, index._cell_capacity
-    new_capacity_total = index.capacity + int(grow.sum().item())
-    # old address -> new address
-    adr = torch.arange(index.capacity, device=dev)
-    cell_of = torch.searchsorted(old_start, adr, right=True) - 1
-    new_adr = adr + shift[cell_of]
-    storage = torch.zeros(index._storage.shape[0], new_capacity_total, 4, dtype=torch.uint8, device=dev)
-    storage[:, new_adr] = index._storage
-    a2i = -torch.ones(new_capacity_total, dtype=torch.long, device=dev)
-    a2i[new_adr] = index._address2id
-    emp = torch.ones(new_capacity_total, dtype=torch.uint8, device=dev)
-    emp[new_adr] = index._is_empty
+    old_cap = index.capacity
+    new_cap = old_cap + int(grow.sum().item())
+    storage = torch.zeros(index._storage.shape[0], new_cap, 4, dtype=torch.uint8, device=dev)
+    a2i = torch.full((new_cap,), -1, dtype=torch.long, device=dev)
+    emp = torch.ones(new_cap, dtype=torch.uint8, device=dev)
+    check(lib.tpq_expand_move(ptr(index._storage), ptr(index._address2id), ptr(index._is_empty), ptr(index._cell_start),
+                              ptr(shift), index.n_cells, index.code_size, old_cap, new_cap,
+                              ptr(storage), ptr(a2i), ptr(emp), _lib.current_stream(dev)))
     for name, val in (("_storage", storage), ("_address2id", a2i), ("_is_empty", emp)):
         delattr(index, name)
         index.register_buffer(name, val)
@@ -151,9 +134,15 @@ def _expand(index, cells: torch.Tensor):
 
 
 def container_add(index, codes: torch.Tensor, cells: torch.Tensor, ids=None, return_address=False):
-    """CellContainer.add (CellContainer.py:313-367)."""
+    """CellContainer.add (CellContainer.py:313-367) on the library's placement kernels (csrc/place.cu): index of
+    appearance, expansion test, write addresses, and one scatter into the reference layout AND the scan layout."""
+    import ctypes as C
+    from . import fn, _lib
+    from ._lib import lib, check, ptr
+    from .index import _fingerprint, _codebook_of
     assert codes.dtype == torch.uint8 and cells.dtype == torch.long
     assert codes.shape[0] == index.code_size and codes.shape[1] == cells.shape[0]
+    assert index._storage is not None, "shard-only index: add to the full index and distribute again"
     dev = index._storage.device
     n = cells.shape[0]
     if ids is None:
@@ -161,32 +150,46 @@ def container_add(index, codes: torch.Tensor, cells: torch.Tensor, ids=None, ret
     else:
         assert ids.dtype == torch.long and ids.shape[0] == n
         ids = ids.to(dev)
-    ioa = _ioa(cells)
+    if n == 0:
+        return (ids, torch.empty(0, dtype=torch.long, device=dev)) if return_address else ids
+    codes, cells = codes.contiguous(), cells.contiguous()
+    assert int(cells.min().item()) >= 0 and int(cells.max().item()) < index.n_cells, "cell id out of range"
+    lay = index._layout
+    fp = lambda: _fingerprint(index._storage, index._is_empty, index._cell_start, index._cell_size, index._address2id,
+                              _codebook_of(index.vq_codec), _codebook_of(index.pq_codec))
+    in_sync = lay is not None and lay.fingerprint == fp()
+    ioa, counts = fn.get_ioa(cells, index.n_cells)
+    prefix = None
     while True:
         # free slots of a cell = capacity - LIVE items.  Without holes live == _cell_size and this is the reference's
-        # `capacity - cell_size - (ioa + 1)` (CellContainer.py:338-341); with holes left by remove() it stops the cell
-        # from expanding while it still has room (and _cell_size, a high-water mark here, from inflating).
-        occupied = torch.cumsum((index._is_empty == 0).to(torch.long), 0)
-        occupied = torch.cat([occupied.new_zeros(1), occupied])
-        live = occupied[index._cell_start + index._cell_capacity] - occupied[index._cell_start]
-        free = index._cell_capacity[cells] - live[cells] - (ioa + 1)
-        need = cells[free < 0].unique()
-        if need.shape[0] == 0:
+        # `capacity - cell_size - (ioa + 1) < 0` test (CellContainer.py:338-341) taken per cell: the largest ioa of a cell
+        # is its count - 1.  With holes left by remove() the empty-slot prefix gives the live count.
+        if index._has_holes:
+            prefix = fn.empty_prefix(index._is_empty)
+            p = prefix.to(torch.long) & 0xFFFFFFFF
+            live = index._cell_capacity - (p[index._cell_start + index._cell_capacity] - p[index._cell_start])
+        else:
+            live = index._cell_size
+        short = counts > index._cell_capacity - live
+        if not bool(short.any().item()):
             break
-        _expand(index, need)
-    empty_adr = torch.nonzero(index._is_empty == 1)[:, 0]           # sorted
-    first_empty = torch.searchsorted(empty_adr, index._cell_start)   # index of each cell's first empty slot
-    write = empty_adr[first_empty[cells] + ioa]
-    M = index.code_size
-    index._storage[:, write] = codes.reshape(M // 4, 4, n).transpose(1, 2)
-    index._address2id[write] = ids
-    if n:
-        index._max_id = max(index._max_id, int(ids.max().item()))
-    index._is_empty[write] = 0
-    # _cell_size = extent the scan must cover = highest occupied slot + 1 (== old + count when the cell has no holes)
-    extent = write - index._cell_start[cells] + 1
-    index._cell_size.scatter_reduce_(0, cells, extent, reduce="amax", include_self=True)
-    index._state_changed()
+        grow = torch.where(short, index._cell_capacity if index.expand_mode == "double"
+                           else torch.full_like(index._cell_capacity, index.expand_step_size), torch.zeros_like(counts))
+        _expand(index, grow)
+        in_sync = False                                              # addresses moved: the scan layout is rebuilt lazily
+    write = fn.get_write_address(cells, ioa, index._cell_start, index._cell_size, index._cell_capacity, prefix)
+    ix = lay.cindex if in_sync else _lib.TpqIndex()
+    if not in_sync:
+        ix.n_subvectors, ix.n_cells, ix.capacity = index.code_size, index.n_cells, index.capacity
+        ix.shard_world = 1
+    ix.cell_start = index._cell_start.data_ptr()
+    check(lib.tpq_store_codes(ptr(codes), ptr(cells), ptr(write), ptr(ids), n, C.byref(ix),
+                              ptr(index._storage), ptr(index._address2id), ptr(index._is_empty), ptr(index._cell_size),
+                              ptr(lay.codes_scan) if in_sync else None, ptr(lay.block_valid) if in_sync else None,
+                              _lib.current_stream(dev)))
+    index._max_id = max(index._max_id, int(ids.max().item()))
+    if not in_sync:                                                  # (in sync: the layout received the same items and stays valid;
+        index._state_changed()                                       #  raw-pointer writes do not move the buffers' fingerprint)
     return (ids, write) if return_address else ids
 
 

@@ -259,6 +259,7 @@ static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp, bool residual = f
 
 struct ScanArgs {
   const uint8_t* codes; const uint32_t* valid; const int32_t* cell_block_start; const int64_t* cell_start;
+  const int64_t* cell_size;
   const float* lut_scan;          // [nq_chunk][MG][256][64] (staged-LUT variant, DSUB == 0)
   const float* x;                 // [d, nq] queries (in-CTA LUT variant)
   const float* cbt;               // pq_codebook_t [256, MP, dsub]
@@ -322,7 +323,11 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
           skip = cp >= 0 && cp < A.n_cells && s == A.cell_start[cp];
         }
         const int b0 = ok ? A.cell_block_start[c] : 0;
-        nb = skip ? 0 : A.cell_block_start[c + 1] - b0;
+        if (!skip) {                                        // the layout holds a block for every slot of the cell's capacity
+          const int have = A.cell_block_start[c + 1] - b0;  // (0 for another shard's cell); the live extent is cell_size
+          const int64_t sz = A.cell_size[c];
+          nb = (int)min((int64_t)have, sz > 0 ? (sz + 31) >> 5 : (int64_t)0);
+        }
         seg_blk0[j] = b0;
         seg_addr0[j] = (uint32_t)s;
         if constexpr (RES) seg_cell[j] = ok ? (int32_t)c : 0;
@@ -600,7 +605,7 @@ static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cel
     A.x = x; A.cbt = ix->pq_codebook_t; A.M = ix->n_subvectors; A.metric = ix->metric;
     A.part2_scan = ix->part2_scan; A.base_sims = base_sims;
     A.codes = ix->codes_scan; A.valid = ix->block_valid; A.cell_block_start = ix->cell_block_start;
-    A.cell_start = ix->cell_start; A.lut_scan = lut_ws; A.cells = cells; A.n_probe_list = npl; A.keys_out = keys;
+    A.cell_start = ix->cell_start; A.cell_size = ix->cell_size; A.lut_scan = lut_ws; A.cells = cells; A.n_probe_list = npl; A.keys_out = keys;
     A.nq = nq; A.q_base = q0; A.n_probe = n_probe; A.k = k; A.kp = kp; A.S = S;
     A.boot_r = 2; A.n_cells = ix->n_cells;
 #ifdef TPQ_DEBUG_KNOBS
@@ -637,7 +642,7 @@ static int check_index(const tpq_index* ix) {
   TPQ_REQUIRE(ix->n_subvectors % 4 == 0, "n_subvectors=%d must be a multiple of 4", ix->n_subvectors);
   TPQ_REQUIRE(ix->metric == TPQ_METRIC_EUCLIDEAN || ix->metric == TPQ_METRIC_COSINE,
               "unsupported distance (reference supports euclidean and cosine only)");
-  TPQ_REQUIRE(ix->vq_codebook && ix->pq_codebook && ix->cell_start && ix->address2id, "index is missing reference buffers");
+  TPQ_REQUIRE(ix->vq_codebook && ix->pq_codebook && ix->cell_start && ix->cell_size && ix->address2id, "index is missing reference buffers");
   TPQ_REQUIRE(ix->codes_scan || ix->n_blocks == 0, "index has no scan layout (call tpq_relayout_codes first)");
   TPQ_REQUIRE(ix->block_valid || ix->n_blocks == 0, "index has no scan layout (block_valid)");
   TPQ_REQUIRE(ix->cell_block_start && ix->pq_codebook_t && ix->pq_norm_t, "index has no scan layout (plan / codebook)");

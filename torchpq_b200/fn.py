@@ -144,3 +144,38 @@ def merge_topk(keys, address2id):
     check(lib.tpq_merge_topk(ptr(keys), nq, n_parts, k, ptr(address2id), address2id.shape[0],
                              ptr(values), ptr(ids), ptr(address), _lib.current_stream(dev)))
     return values, ids, address
+
+
+# ------------------------------------------------------------------ build side (CellContainer.add, CellContainer.py:313-367)
+def get_ioa(cells, n_cells):
+    """get_ioa (kernels/cuda/get_ioa.cu:8-47): cells [n] i64 -> (ioa [n] i64, counts [n_cells] i64)."""
+    assert cells.dtype == torch.int64 and cells.dim() == 1 and cells.device.type == "cuda"
+    cells = cells.contiguous()
+    n, dev = cells.shape[0], cells.device
+    ioa = torch.empty(n, dtype=torch.long, device=dev)
+    counts = torch.empty(n_cells, dtype=torch.long, device=dev)
+    ws_bytes = lib.tpq_ioa_workspace_bytes(n, n_cells)
+    ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
+    check(lib.tpq_get_ioa(ptr(cells), n, n_cells, ptr(ioa), ptr(counts), ptr(ws), ws_bytes, _lib.current_stream(dev)))
+    return ioa, counts
+
+
+def empty_prefix(is_empty):
+    """prefix[a] = number of empty slots in [0, a), a = 0..capacity  (int32-viewed uint32)."""
+    assert is_empty.dtype == torch.uint8 and is_empty.device.type == "cuda"
+    is_empty = is_empty.contiguous()
+    cap, dev = is_empty.shape[0], is_empty.device
+    prefix = torch.empty(cap + 1, dtype=torch.int32, device=dev)
+    ws_bytes = lib.tpq_empty_prefix_workspace_bytes(cap)
+    ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
+    check(lib.tpq_empty_prefix(ptr(is_empty), cap, ptr(prefix), ptr(ws), ws_bytes, _lib.current_stream(dev)))
+    return prefix
+
+
+def get_write_address(cells, ioa, cell_start, cell_size, cell_capacity, prefix=None):
+    """get_write_address (kernels/cuda/get_write_address_v2.cu:9-41): the ioa-th empty slot of each item's cell."""
+    n, dev = cells.shape[0], cells.device
+    out = torch.empty(n, dtype=torch.long, device=dev)
+    check(lib.tpq_get_write_address(ptr(cells), ptr(ioa), n, ptr(cell_start), ptr(cell_size), ptr(cell_capacity),
+                                    cell_start.shape[0], ptr(prefix), ptr(out), _lib.current_stream(dev)))
+    return out

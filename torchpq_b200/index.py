@@ -54,7 +54,10 @@ class ScanLayout:
             assert t is not None and t.is_contiguous()
         if parts is None:
             self.cell_block_start = torch.empty(Cn + 1, dtype=torch.int32, device=dev)
-            check(lib.tpq_relayout_plan(ptr(index._cell_size), Cn, shard_rank, shard_world,
+            # blocks for every slot of each cell's CAPACITY, so that add() can place new items in the layout in place
+            extent = getattr(index, "_cell_capacity", None)
+            extent = index._cell_size if extent is None else extent
+            check(lib.tpq_relayout_plan(ptr(extent), Cn, shard_rank, shard_world,
                                         ptr(self.cell_block_start), stream))
             self.n_blocks = int(self.cell_block_start[Cn].item())          # one host sync per (re)build
             self.codes_scan = torch.empty(max(1, lib.tpq_codes_scan_bytes(M, self.n_blocks)), dtype=torch.uint8, device=dev)
@@ -133,6 +136,7 @@ class IVFPQIndex(StateModule):
         self.use_smart_probing = True                                    # IVFPQIndex.py:58
         self.smart_probing_temperature = 30.0                            # IVFPQIndex.py:59
         self._max_id = -1
+        self._has_holes = False                                         # set by remove(): add() then needs the empty-slot prefix
         dev = torch.device(device)
         cap = n_cells * initial_size
         self.register_buffer("_address2id", -torch.ones(cap, dtype=torch.long, device=dev))
@@ -175,6 +179,7 @@ class IVFPQIndex(StateModule):
         buffers: ``_max_id`` (BaseContainer.py:30,49-51) is re-derived from ``_address2id`` so that ids handed out
         after a load do not restart at 0 and ``get_address_by_id`` sizes its inverse map correctly."""
         super().load_state_dict(state_dict, strict)
+        self._has_holes = True                                          # unknown provenance: assume the container may have holes
         self._refresh_max_id()
 
     def _refresh_max_id(self):
@@ -360,6 +365,7 @@ class IVFPQIndex(StateModule):
             return
         self._is_empty[address] = 1
         self._address2id[address] = -1
+        self._has_holes = True
         self._state_changed()
 
     def encode(self, x):
