@@ -32,7 +32,7 @@ def test_empty_prefix_and_write_address_with_holes(cuda_device):
     expect[1:] = np.cumsum(is_empty, dtype=np.int64)
     assert np.array_equal(prefix, expect)
     start = np.arange(C, dtype=np.int64) * cap_cell
-    free = np.array([is_empty[s:s + cap_cell].sum() for s in start])
+    free = np.array([int(is_empty[s:s + cap_cell].sum()) for s in start], dtype=np.int64)
     cells = np.repeat(np.arange(C), np.minimum(free, 20))
     rng.shuffle(cells)
     ioa = O.get_ioa(cells)

@@ -16,13 +16,18 @@ def make_residual_index(st, device="cuda:0"):
     return ix.load_state(st)
 
 
-@pytest.mark.parametrize("M,d,smart", [(8, 32, True), (64, 128, False), (16, 64, True)])
-def test_residual_search_matches_oracle_and_reference_kernel(cuda_device, M, d, smart):
+@pytest.mark.parametrize("M,d,smart,nq", [
+    (8, 32, True, 64), (64, 128, False, 64), (16, 64, True, 64),     # query half of the LUT built in the CTA (d/M 4, 2, 4)
+    (96, 192, True, 40), (120, 240, False, 40),                      # M > 64: staged query half, one table per CTA
+    (8, 24, True, 40), (64, 512, True, 24), (120, 960, True, 16),    # d/M = 3, 8, 8
+    (16, 64, False, 3), (96, 192, True, 2),                          # tiny batches: every query is cut into slices
+])
+def test_residual_search_matches_oracle_and_reference_kernel(cuda_device, M, d, smart, nq):
     torch.manual_seed(M)
     base = torch.randn(d, 5000)
-    st = B.build_state_residual(base, M, 16)
+    st = B.build_state_residual(base, M, 16, vq_iters=3, pq_iters=2 if M > 64 else 3)
     st.n_probe, st.use_smart_probing = 6, smart
-    x = torch.randn(d, 64)
+    x = torch.randn(d, nq)
     k = 20
     ov, oi, oa = O.search_residual(st, x, k=k + 1, return_address=True)
     ix = make_residual_index(st)

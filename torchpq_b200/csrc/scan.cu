@@ -37,6 +37,7 @@ namespace tpq {
 // CTA = 256 codes x 16 sub-quantizers x LS_QT queries: every codebook value is loaded once (coalesced over the
 // code) and reused for LS_QT queries; query sub-vectors are broadcast from shared memory.
 constexpr int LS_QT = 8, LS_MT = 16;
+constexpr int kLutPart1 = 2;          // lut_scan_kernel `metric` value: the query half of the residual LUT
 __global__ void __launch_bounds__(256)
 lut_scan_kernel(const float* __restrict__ x, const float* __restrict__ cb, int d, int M, int MP, int nq,
                 int q_base, int n_chunk, int metric, float* __restrict__ lut_scan) {
@@ -85,6 +86,7 @@ lut_scan_kernel(const float* __restrict__ x, const float* __restrict__ cb, int d
       if (m < M) {
         y = dot[qq];
         if (metric == TPQ_METRIC_EUCLIDEAN) y = __fsub_rn(__fsub_rn(__fmul_rn(dot[qq], 2.f), a2s[qq * LS_MT + mm]), b2);
+        else if (metric == kLutPart1) y = __fmul_rn(dot[qq], 2.f);   // residual IVFPQ: part1 = 2 <x_m, p> (IVFPQIndex.py:377)
       }
       lut_scan[((size_t)(q0 + qq) * MG + g) * 16384 + c * 64 + sl] = y;
     }
@@ -239,10 +241,10 @@ struct Scanner {
 };
 
 struct ScanSmem { size_t lut, part1, seg_blk0, seg_addr0, seg_cell, seg_prefix, thr, lock, rep, list, bufs, total; };
-static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp, bool residual = false) {
+static ScanSmem scan_smem(int MP, int n_probe, int nw, int kp, bool residual = false, bool part1_in_smem = false) {
   ScanSmem s; size_t off = 0;
   s.lut = off;        off += (size_t)((MP + 63) / 64) * 65536;
-  s.part1 = off;      off += residual ? (size_t)((MP + 63) / 64) * 65536 : 0;   // query half of the residual LUT
+  s.part1 = off;      off += (residual && part1_in_smem) ? (size_t)((MP + 63) / 64) * 65536 : 0;   // query half of the residual LUT
   s.seg_cell = off;   off += residual ? (size_t)n_probe * 4 : 0;
   s.seg_blk0 = off;   off += (size_t)n_probe * 4;
   s.seg_addr0 = off;  off += (size_t)n_probe * 4;
@@ -339,7 +341,9 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
-  if constexpr (DSUB == 0) {
+  if constexpr (DSUB == 0 && RES) {
+    // residual with a staged query half: part1 stays in global memory (L2) and is added to part2 cell by cell
+  } else if constexpr (DSUB == 0) {
     // --- stage LUT (MG * 64 KB, coalesced 16-byte copies)
     const float4* src = reinterpret_cast<const float4*>(A.lut_scan + (size_t)qi * MG * 16384);
     float4* dst = reinterpret_cast<float4*>(lut);
@@ -423,17 +427,19 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
   CtaTopK& tk = sc.tk;
   uint64_t* bufs = reinterpret_cast<uint64_t*>(smem + L.bufs);
   if constexpr (RES) {
-    const float4* p1 = reinterpret_cast<const float4*>(smem + L.part1);
+    // query half of the LUT: the shared-memory table built above (DSUB > 0), or the staged copy in global memory
+    const float4* p1 = DSUB > 0 ? reinterpret_cast<const float4*>(smem + L.part1)
+                                : reinterpret_cast<const float4*>(A.lut_scan + (size_t)qi * MG * 16384);
     float4* dst = reinterpret_cast<float4*>(lut);
     for (int j = 0; j < P; ++j) {
-      const int b0 = seg_prefix[j], b1 = seg_prefix[j + 1];
-      if (b1 == b0) continue;                                          // skipped entry, empty cell or another shard's cell
+      const int b0 = max(seg_prefix[j], b_begin), b1 = min(seg_prefix[j + 1], b_end);
+      if (b1 <= b0) continue;                                          // skipped entry, empty cell, another shard's or slice's blocks
       __syncthreads();                                                 // every warp is done with the previous cell's LUT
       if (tid == 0) *sc.next = b0;
       const float4* p2 = reinterpret_cast<const float4*>(A.part2_scan + (size_t)seg_cell[j] * MG * 16384);
       #pragma unroll 4
       for (int i = tid; i < MG * 4096; i += NW * 32) {                 // store_precomputed_to_smem: part1 + part2 (:609-628)
-        const float4 a = p1[i], b = __ldg(p2 + i);
+        const float4 a = DSUB > 0 ? p1[i] : __ldg(p1 + i), b = __ldg(p2 + i);
         dst[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
       }
       __syncthreads();
@@ -441,7 +447,7 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       sc.run(b1);
     }
     tk.cta_drain(bufs, lane, warp);
-    uint64_t* outr = A.keys_out + (size_t)q * A.k;
+    uint64_t* outr = A.keys_out + ((size_t)q * A.S + slice) * A.k;
     for (int i = tid; i < A.k; i += NW * 32) outr[i] = tk.list[i];
     return;
   }
@@ -540,7 +546,6 @@ static unsigned long long* g_phase = nullptr;     // device buffer set by tpq_de
 static int pick_slices(const tpq_index* ix, int nq, int k) {
   // enough CTAs for ~2 waves of 2 CTAs/SM when the batch is small
   (void)k;
-  if (ix->residual) return 1;                                 // the residual kernel walks whole probe lists
   const int want = 148 * 4;
   if (nq >= want) return 1;
   int s = (want + nq - 1) / nq;
@@ -556,6 +561,8 @@ static int fused_dsub(const tpq_index* ix) {
   const char* mode = getenv("TPQ_LUT_MODE");
   if (mode && !strcmp(mode, "staged")) return 0;
 #endif
+  // residual IVFPQ keeps TWO tables when the query half is built in the CTA: that fits for M <= 64 and pays for d/M <= 4
+  if (ix->residual && (ix->m_pad > 64 || dsub == 8)) return 0;
   return (dsub == 1 || dsub == 2 || dsub == 4 || dsub == 8) ? dsub : 0;
 }
 
@@ -583,7 +590,7 @@ static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cel
                          int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st,
                          const float* base_sims = nullptr) {
   const int kp = next_pow2(k < 32 ? 32 : k);
-  ScanSmem L = scan_smem(MP, n_probe, NW, kp, RES);
+  ScanSmem L = scan_smem(MP, n_probe, NW, kp, RES, RES && DSUB > 0);
   if (L.total > 227 * 1024) {
     set_error("scan: M=%d n_probe=%d k=%d needs %zu B of shared memory (> 227 KB)", ix->n_subvectors, n_probe, k, L.total);
     return TPQ_ERR_UNSUPPORTED;
@@ -598,7 +605,7 @@ static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cel
       size_t xs_bytes = (size_t)LS_QT * LS_MT * (dsub + 1) * 4;
       dim3 lgrid((n + LS_QT - 1) / LS_QT, (MP + LS_MT - 1) / LS_MT);
       lut_scan_kernel<<<lgrid, 256, xs_bytes, st>>>(x, ix->pq_codebook, ix->d_vector, ix->n_subvectors, MP,
-                                                    nq, q0, n, ix->metric, lut_ws);
+                                                    nq, q0, n, RES ? kLutPart1 : ix->metric, lut_ws);
       TPQ_LAUNCH_CHECK("lut_scan_kernel");
     }
     ScanArgs A;
@@ -655,17 +662,30 @@ static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cel
                          int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st,
                          const float* base_sims = nullptr) {
   if (ix->residual) {
-    // residual IVFPQ: two 64 KB tables per CTA -> one 16-warp CTA per SM; M <= 64 and d/M in {1,2,4} for now
+    // residual IVFPQ.  M <= 64 and d/M in {1,2,4}: the query half of the LUT is built once into a second shared-memory
+    // table (two 64 KB tables -> one 16-warp CTA per SM).  Otherwise (M up to 192, any d/M) the query half is staged in
+    // global memory by lut_scan_kernel and added to the per-cell half straight from L2, so one table suffices.
     const int dsub = ix->d_vector / ix->n_subvectors;
     if (!ix->part2_scan || !base_sims) { set_error("residual search needs part2_scan and base_sims"); return TPQ_ERR_BAD_ARG; }
     if (ix->metric != TPQ_METRIC_EUCLIDEAN) { set_error("residual IVFPQ is defined for the euclidean metric"); return TPQ_ERR_UNSUPPORTED; }
-    if (ix->m_pad > 64 || !(dsub == 1 || dsub == 2 || dsub == 4)) {
-      set_error("residual IVFPQ: n_subvectors=%d, d_subvector=%d not supported yet (need M <= 64, d/M in {1,2,4})", ix->n_subvectors, dsub);
-      return TPQ_ERR_UNSUPPORTED;
-    }
 #define TPQ_RES(MPv, DS) launch_scan_d<MPv, 16, 1, DS, true>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, base_sims)
-    if (ix->m_pad == 32) return dsub == 1 ? TPQ_RES(32, 1) : dsub == 2 ? TPQ_RES(32, 2) : TPQ_RES(32, 4);
-    return dsub == 1 ? TPQ_RES(64, 1) : dsub == 2 ? TPQ_RES(64, 2) : TPQ_RES(64, 4);
+    switch (fused_dsub(ix)) {
+      case 1: return ix->m_pad == 32 ? TPQ_RES(32, 1) : TPQ_RES(64, 1);
+      case 2: return ix->m_pad == 32 ? TPQ_RES(32, 2) : TPQ_RES(64, 2);
+      case 4: return ix->m_pad == 32 ? TPQ_RES(32, 4) : TPQ_RES(64, 4);
+      default: break;
+    }
+    switch (ix->m_pad) {
+      case 32:  return TPQ_RES(32, 0);
+      case 64:  return TPQ_RES(64, 0);
+      case 96:  return TPQ_RES(96, 0);
+      case 128: return TPQ_RES(128, 0);
+      case 160: return TPQ_RES(160, 0);
+      case 192: return TPQ_RES(192, 0);
+      default:
+        set_error("residual IVFPQ: n_subvectors=%d (padded %d) > 192 is not supported", ix->n_subvectors, ix->m_pad);
+        return TPQ_ERR_UNSUPPORTED;
+    }
 #undef TPQ_RES
   }
 #define TPQ_SCAN_ARGS ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st
