@@ -533,7 +533,7 @@ static int launch_merge(const uint64_t* keys_in, int nq, int n_parts, int k, int
 constexpr int kQueryChunk = 16384;    // queries per scan launch (bounds the LUT workspace: 64 KB * MG each)
 
 // optional CUDA-event timing of the scan launches (bench.py's roofline leg); off by default
-constexpr int kProfMax = 64;
+constexpr int kProfMax = 1024;
 static bool g_prof_on = false;
 static int g_prof_n = 0;
 static cudaEvent_t g_prof_start[kProfMax], g_prof_stop[kProfMax];

@@ -119,10 +119,12 @@ class IVFPQIndex(StateModule):
             "the reference can only build/search euclidean and cosine IVFPQ indexes (MultiKMeans.py:82-115,218-223)"
         if pq_use_residual:
             assert distance == "euclidean", "residual IVFPQ is defined on euclidean residuals"
-            # IVFPQIndex.py:52-55: the per-cell table is precomputed when it fits 4 GB; the on-the-fly variant
-            # (precomputed_adc_residual, IVFPQIndex.py:382-405) is not built here
-            if n_cells * 256 * n_subvectors * 4 > 4 * 1024 ** 3:
-                raise NotImplementedError("residual IVFPQ without the precomputed part-2 table is not supported")
+            # IVFPQIndex.py:52-55: the reference precomputes the per-cell half of the LUT when it fits 4 GB and otherwise
+            # recomputes it per (query, probe) (precomputed_adc_residual, :382-405) -- a device-memory limit of 2021.  On a
+            # 180 GB part the table (n_cells * ceil(M/64) * 64 KB in scan layout) is simply kept, up to 64 GB; the two
+            # variants differ only in fp32 association, (2xp) + (-2cp - |p|^2) vs (2xp - |p|^2) + (-2cp).
+            if n_cells * 256 * ((n_subvectors + 63) // 64 * 64) * 4 > 64 * 1024 ** 3:
+                raise NotImplementedError("residual IVFPQ: the precomputed part-2 table would exceed 64 GB")
         if initial_size is None:
             initial_size = expand_step_size                              # CellContainer.py:23-24
         assert initial_size >= 0 and n_cells > 0
