@@ -490,7 +490,31 @@ def secondary_block(device, threads, c3_index, c3_xs_dev, k3, steps):
             centres = cluster_centres(wl[1], wl[3], device) if clustered else None
             sec[name] = measure_single_gpu(name, index, base, device, 10000, steps, threads, centres=centres)
             if name == "c3c":
-                sec[name]["note"] = "queries drawn from the same Gaussian mixture as the base: recall is meaningful and smart probing prunes"
+                # smart probing at the reference's default temperature (30) never prunes on these distances; a user who
+                # wants pruning lowers `smart_probing_temperature` -- same index, same queries, ours vs the CPU oracle again
+                sweep = []
+                xs_c = [x.to(device) for x in gen_queries(wl[1], 10000, 4, device, centres=centres)]
+                truth_c = exact_truth(base, xs_c[0][:, :1000].contiguous(), wl[5], wl[6])
+                for temp in (1.0, 0.3, 0.1):
+                    index.smart_probing_temperature = temp
+                    ms = cuda_time(lambda i: index.search(xs_c[i % 4], k=wl[5]), 5, device=device)
+                    _, _, npl = T.fn.coarse_probe(xs_c[0], index.vq_codec.codebook, wl[4], True, temp)
+                    ids_t = index.search(xs_c[0][:, :1000].contiguous(), k=wl[5])[1]
+                    row = {"temperature": temp, "queries_per_s": 10000 / ms * 1e3,
+                           "mean_n_probe_list": float(npl.clamp(1, wl[4]).float().mean().item()),
+                           "recall_at_100": recall(ids_t, truth_c)}
+                    try:
+                        st_c = to_oracle_state(index)
+                        _, oi, _ = oracle_search(st_c, xs_c[0][:, :200].cpu().contiguous(), wl[5], threads)
+                        row["rows_with_identical_id_sets_vs_oracle_200q"] = float(
+                            (np.sort(ids_t[:200].cpu().numpy(), 1) == np.sort(oi, 1)).all(axis=1).mean())
+                    except Exception as e:
+                        row["oracle_error"] = repr(e)
+                    sweep.append(row)
+                index.smart_probing_temperature = 30.0
+                sec[name]["smart_probing_temperature_sweep"] = sweep
+                sec[name]["note"] = ("queries drawn from the same Gaussian mixture as the base: recall is meaningful; "
+                                     "smart probing prunes once the temperature is lowered from the reference default of 30")
             del index, base
             torch.cuda.empty_cache()
         except Exception as e:
@@ -548,6 +572,8 @@ def main():
     ap.add_argument("--cpu-sample", type=float, default=12.0, help="seconds of CPU-oracle work for cpu_baseline")
     ap.add_argument("--query-groups", type=int, default=0,
                     help="multi-GPU grid: ranks = cell_shards x query_groups (0 = auto: 1 up to 4 GPUs, 2 at 8)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU key exchange: fused scan + P2P push into symmetric memory (auto/p2p) or NCCL all-gather")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary block (c2/c4/c3c/C5/build/reference kernel)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -570,6 +596,7 @@ def main():
     config = {"workload": f"{args.workload}: {desc}", "n_query_per_step": args.nq,
               "index_sharding": f"cells mod {shards}" + (f" x {groups} query groups" if groups > 1 else ""),
               "use_smart_probing": not args.no_smart,
+              "exchange": ("fused scan + P2P key push (symmetric memory) + barrier" if args.exchange != "nccl" else "NCCL all-gather") if world > 1 else "none",
               "l2_policy": "inputs larger than L2 (code store >= 640 MB vs 126 MB L2; 4 rotating query batches)",
               "training": f"seeded k-means, <= {VQ_ITERS} (coarse) / {PQ_ITERS} (PQ) Lloyd iterations, tol 1e-4 (the reference's settings)"}
 
@@ -629,7 +656,7 @@ def main():
 
     def search(x):
         if world > 1:
-            return tdist.sharded_search(index, x, k, grid=grid, coarse_group=coarse_group)
+            return tdist.sharded_search(index, x, k, grid=grid, coarse_group=coarse_group, exchange=args.exchange)
         return index.search(x, k=k)
 
     def step_device(i):

@@ -201,6 +201,18 @@ int tpq_expand_move(const uint8_t* old_storage, const int64_t* old_address2id, c
 int tpq_profile_enable(int on);
 int tpq_profile_scan_ms(float* total_ms, int* n_launches);
 
+/* ------------------------------------------------------------------ fused scan + exchange (multi-GPU)
+ * The scan of tpq_ivfpq_search(_cells) with its output fused into the cross-shard exchange: every CTA stores its sorted
+ * top-k keys straight into slot `my_slot` of each rank's gather buffer peer_keys[p] ([n_slots, nq, k] u64 in peer-mapped
+ * memory, e.g. torch symmetric memory) over NVLink, instead of a local buffer that a collective would copy afterwards.
+ * The caller then synchronises the ranks (symmetric-memory barrier) and runs tpq_merge_topk on its own buffer.
+ * cells == NULL: the coarse probe runs inside (x as given to search); else x / cells / base_sims / n_probe_list as for
+ * tpq_ivfpq_search_cells.  TPQ_ERR_UNSUPPORTED when the batch is small enough to be sliced (use the gathered path). */
+int tpq_ivfpq_scan_push(const tpq_index* index, const float* x_dn, const int64_t* cells, const float* base_sims,
+                        const int64_t* n_probe_list, int nq, int n_probe, int k, int smart, float temperature,
+                        uint64_t* const* peer_keys, int n_peers, int my_slot,
+                        void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ cross-shard merge
  * keys_in [n_parts, nq, k] (the all-gather's layout; each part sorted descending, 0 = empty slot) -> top-k per query,
  * decoded: values (-inf pad), address (-1 pad), ids = address2id[address] (BaseContainer.py:58-65). */

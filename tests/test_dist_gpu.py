@@ -45,7 +45,24 @@ def _worker(rank, world, port, q):
         if grid == (2, 1):
             lay = full.layout()
             ok = ok and lay.n_blocks < ix.layout().n_blocks + 64 and full.resident_bytes() > 0
-    q.put((rank, bool(ok)))
+    # fused scan + exchange (P2P key push into every rank's symmetric-memory gather buffer) == the NCCL all-gather path,
+    # on a batch large enough not to be sliced, several steps in a row (the two gather buffers alternate)
+    xb = torch.randn(64, 1500, generator=torch.Generator().manual_seed(11)).to(f"cuda:{rank}")
+    ref = tdist.sharded_search(full, xb, 25, return_address=True, grid=(1, 2), split_coarse=False, exchange="nccl")
+    p2p = "unavailable"
+    try:
+        for grid, split in (((1, 2), False), ((2, 1), True), ((2, 1), False)):
+            ix2 = T.IVFPQIndex(64, 16, 32, initial_size=1, device=f"cuda:{rank}")
+            if rank == 0:
+                ix2.load_state(st)
+            tdist.distribute(ix2, 0, grid=grid)
+            for _ in range(3):
+                got = tdist.sharded_search(ix2, xb, 25, return_address=True, grid=grid, split_coarse=split, exchange="p2p")
+                ok = ok and all(torch.equal(a_, b_) for a_, b_ in zip(got, ref))
+        p2p = "ok"
+    except AssertionError as e:
+        p2p = f"unavailable: {e}"
+    q.put((rank, bool(ok), p2p))
     dist.destroy_process_group()
 
 
@@ -62,4 +79,6 @@ def test_sharded_search_nccl():
     res = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(0, True), (1, True)]
+    print("fused exchange:", [r[2] for r in res])
+    assert sorted(r[:2] for r in res) == [(0, True), (1, True)]
+    assert all(r[2] == "ok" for r in res), res

@@ -68,6 +68,7 @@ SIGNATURES = {
     "tpq_profile_enable": (_I, [_I]),
     "tpq_profile_scan_ms": (_I, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "tpq_merge_topk": (_I, [_P, _I, _I, _I, _P, _I64, _P, _P, _P, _P]),
+    "tpq_ivfpq_scan_push": (_I, [_IX, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _I, _P, _SZ, _P]),
     "tpq_ioa_workspace_bytes": (_SZ, [_I64, _I]),
     "tpq_get_ioa": (_I, [_P, _I64, _I, _P, _P, _P, _SZ, _P]),
     "tpq_empty_prefix_workspace_bytes": (_SZ, [_I64]),

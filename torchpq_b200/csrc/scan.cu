@@ -271,6 +271,8 @@ struct ScanArgs {
   const int64_t* cells;           // [nq, n_probe]
   const int64_t* n_probe_list;    // [nq]
   uint64_t* keys_out;             // [nq, S, k]
+  uint64_t* peer_keys[8];         // fused exchange: every rank's gather buffer [world, nq, k] (NVLink peer memory)
+  int n_peers, peer_slot;         // n_peers == 0: keys go to keys_out
   int nq, q_base, n_probe, k, kp, S;
   int boot_r;                     // blocks per warp in the bootstrap (1 or 2)
   int n_cells;                    // probe entries outside [0, n_cells) are treated as empty segments
@@ -279,6 +281,24 @@ struct ScanArgs {
   int boot_mode;                  // 1 = merge-tree bootstrap (A/B against the quick start)
 #endif
 };
+
+// The CTA's sorted top-k keys leave the SM here.  Fused exchange (n_peers > 0, dist.py): instead of a local buffer that an
+// NCCL all-gather would then copy, the CTA stores its k keys straight into slot `peer_slot` of EVERY rank's gather buffer
+// over NVLink (coalesced 8-byte stores, k * 8 B per peer), so the transfer overlaps the scans still running; a
+// symmetric-memory barrier and the merge kernel follow.
+template <int NW>
+__device__ __forceinline__ void write_keys(const ScanArgs& A, const uint64_t* list, int q, int slice, int tid) {
+  if (A.n_peers > 0) {
+    const size_t o = ((size_t)A.peer_slot * A.nq + q) * A.k;
+    for (int p = 0; p < A.n_peers; ++p) {
+      uint64_t* out = A.peer_keys[p] + o;
+      for (int i = tid; i < A.k; i += NW * 32) out[i] = list[i];
+    }
+    return;
+  }
+  uint64_t* out = A.keys_out + ((size_t)q * A.S + slice) * A.k;
+  for (int i = tid; i < A.k; i += NW * 32) out[i] = list[i];
+}
 
 // DSUB > 0: the CTA builds its query's LUT itself from the (L2-resident) transposed codebook -- no LUT
 // round trip through HBM, no LUT workspace.  DSUB == 0: the LUT was written by lut_scan_kernel and is copied in.
@@ -447,8 +467,7 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
       sc.run(b1);
     }
     tk.cta_drain(bufs, lane, warp);
-    uint64_t* outr = A.keys_out + ((size_t)q * A.S + slice) * A.k;
-    for (int i = tid; i < A.k; i += NW * 32) outr[i] = tk.list[i];
+    write_keys<NW>(A, tk.list, q, slice, tid);
     return;
   }
   // bootstrap: the first R blocks of every warp go to the list unfiltered through one register sort per warp and a
@@ -476,8 +495,7 @@ ivfpq_scan_kernel(ScanArgs A, ScanSmem L) {
 #ifdef TPQ_DEBUG_KNOBS
   if (A.phase && tid == 0) atomicAdd(A.phase + 4, 1ull);
 #endif
-  uint64_t* out = A.keys_out + ((size_t)q * A.S + slice) * A.k;
-  for (int i = tid; i < A.k; i += NW * 32) out[i] = tk.list[i];
+  write_keys<NW>(A, tk.list, q, slice, tid);
 }
 
 // ----------------------------------------------------------------------------- merge + decode
@@ -566,6 +584,8 @@ static int fused_dsub(const tpq_index* ix) {
   return (dsub == 1 || dsub == 2 || dsub == 4 || dsub == 8) ? dsub : 0;
 }
 
+struct PeerOut { uint64_t* keys[8]; int n, slot; };
+
 struct SearchWs {
   size_t coarse, probe_sims, cells, npl, xnorm, lut, keys, total;
 };
@@ -588,7 +608,7 @@ static SearchWs search_ws(const tpq_index* ix, int nq, int n_probe, int k) {
 template <int MP, int NW, int MINB, int DSUB, bool RES = false>
 static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cells, const int64_t* npl,
                          int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st,
-                         const float* base_sims = nullptr) {
+                         const float* base_sims = nullptr, const PeerOut* peers = nullptr) {
   const int kp = next_pow2(k < 32 ? 32 : k);
   ScanSmem L = scan_smem(MP, n_probe, NW, kp, RES, RES && DSUB > 0);
   if (L.total > 227 * 1024) {
@@ -615,6 +635,8 @@ static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cel
     A.cell_start = ix->cell_start; A.cell_size = ix->cell_size; A.lut_scan = lut_ws; A.cells = cells; A.n_probe_list = npl; A.keys_out = keys;
     A.nq = nq; A.q_base = q0; A.n_probe = n_probe; A.k = k; A.kp = kp; A.S = S;
     A.boot_r = 2; A.n_cells = ix->n_cells;
+    A.n_peers = 0; A.peer_slot = 0;
+    if (peers) { A.n_peers = peers->n; A.peer_slot = peers->slot; for (int p = 0; p < peers->n; ++p) A.peer_keys[p] = peers->keys[p]; }
 #ifdef TPQ_DEBUG_KNOBS
     { const char* br = getenv("TPQ_BOOT_R"); if (br && atoi(br) == 1) A.boot_r = 1; }
     A.phase = g_phase;
@@ -632,13 +654,13 @@ static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cel
 
 template <int MP, int NW, int MINB>
 static int launch_scan(const tpq_index* ix, const float* x, const int64_t* cells, const int64_t* npl,
-                       int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st) {
+                       int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st, const PeerOut* peers) {
   switch (fused_dsub(ix)) {
-    case 1:  return launch_scan_d<MP, NW, MINB, 1>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
-    case 2:  return launch_scan_d<MP, NW, MINB, 2>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
-    case 4:  return launch_scan_d<MP, NW, MINB, 4>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
-    case 8:  return launch_scan_d<MP, NW, MINB, 8>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
-    default: return launch_scan_d<MP, NW, MINB, 0>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st);
+    case 1:  return launch_scan_d<MP, NW, MINB, 1>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, nullptr, peers);
+    case 2:  return launch_scan_d<MP, NW, MINB, 2>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, nullptr, peers);
+    case 4:  return launch_scan_d<MP, NW, MINB, 4>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, nullptr, peers);
+    case 8:  return launch_scan_d<MP, NW, MINB, 8>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, nullptr, peers);
+    default: return launch_scan_d<MP, NW, MINB, 0>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, nullptr, peers);
   }
 }
 
@@ -660,7 +682,7 @@ static int check_index(const tpq_index* ix) {
 
 static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cells, const int64_t* npl,
                          int nq, int n_probe, int k, int S, float* lut_ws, uint64_t* keys, cudaStream_t st,
-                         const float* base_sims = nullptr) {
+                         const float* base_sims = nullptr, const PeerOut* peers = nullptr) {
   if (ix->residual) {
     // residual IVFPQ.  M <= 64 and d/M in {1,2,4}: the query half of the LUT is built once into a second shared-memory
     // table (two 64 KB tables -> one 16-warp CTA per SM).  Otherwise (M up to 192, any d/M) the query half is staged in
@@ -668,7 +690,7 @@ static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cel
     const int dsub = ix->d_vector / ix->n_subvectors;
     if (!ix->part2_scan || !base_sims) { set_error("residual search needs part2_scan and base_sims"); return TPQ_ERR_BAD_ARG; }
     if (ix->metric != TPQ_METRIC_EUCLIDEAN) { set_error("residual IVFPQ is defined for the euclidean metric"); return TPQ_ERR_UNSUPPORTED; }
-#define TPQ_RES(MPv, DS) launch_scan_d<MPv, 16, 1, DS, true>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, base_sims)
+#define TPQ_RES(MPv, DS) launch_scan_d<MPv, 16, 1, DS, true>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, base_sims, peers)
     switch (fused_dsub(ix)) {
       case 1: return ix->m_pad == 32 ? TPQ_RES(32, 1) : TPQ_RES(64, 1);
       case 2: return ix->m_pad == 32 ? TPQ_RES(32, 2) : TPQ_RES(64, 2);
@@ -688,7 +710,7 @@ static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cel
     }
 #undef TPQ_RES
   }
-#define TPQ_SCAN_ARGS ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st
+#define TPQ_SCAN_ARGS ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, peers
 #ifdef TPQ_DEBUG_KNOBS
   // tuning knob for experiments (scripts/sweep_scan.py): TPQ_SCAN_CFG = "<warps>x<min CTAs/SM>"
   const char* cfg = getenv("TPQ_SCAN_CFG");
@@ -803,6 +825,43 @@ extern "C" int tpq_ivfpq_search(const tpq_index* ix, const float* x_dn, int nq, 
   uint64_t* keys = reinterpret_cast<uint64_t*>(w + W.keys);
   if (int rc = scan_dispatch(ix, x, cells, npl, nq, n_probe, k, S, reinterpret_cast<float*>(w + W.lut), keys, st, probe_sims)) return rc;
   return launch_merge(keys, nq, S, k, k, (int64_t)S * k, ix->address2id, ix->capacity, values, ids, address, keys_out, st);
+}
+
+extern "C" int tpq_ivfpq_scan_push(const tpq_index* ix, const float* x_dn, const int64_t* cells, const float* base_sims,
+                                   const int64_t* n_probe_list, int nq, int n_probe, int k, int smart, float temperature,
+                                   uint64_t* const* peer_keys, int n_peers, int my_slot,
+                                   void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = check_index(ix)) return rc;
+  TPQ_REQUIRE(0 < k && k <= 1024, "k must be in (0, 1024], got %d", k);
+  TPQ_REQUIRE(nq >= 0 && n_probe >= 1 && x_dn, "bad query batch");
+  TPQ_REQUIRE(peer_keys && n_peers >= 1 && n_peers <= 8 && my_slot >= 0, "tpq_ivfpq_scan_push: bad peer list");
+  TPQ_REQUIRE((cells == nullptr) == (n_probe_list == nullptr), "cells and n_probe_list go together");
+  if (nq == 0) return TPQ_OK;
+  if (pick_slices(ix, nq, k) != 1) { set_error("tpq_ivfpq_scan_push: batch of %d queries is sliced; use the gathered exchange", nq); return TPQ_ERR_UNSUPPORTED; }
+  if (nq > kQueryChunk) { set_error("tpq_ivfpq_scan_push: at most %d queries per call", kQueryChunk); return TPQ_ERR_UNSUPPORTED; }
+  SearchWs W = search_ws(ix, nq, n_probe, k);
+  if (!ws || ws_bytes < W.total) { set_error("workspace too small (%zu < %zu)", ws_bytes, W.total); return TPQ_ERR_WORKSPACE; }
+  uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+  const float* x = x_dn;
+  if (!cells) {                                                       // the whole coarse stage runs here (replicated probe)
+    TPQ_REQUIRE(n_probe <= ix->n_cells, "n_probe=%d must be in [1, n_cells=%d]", n_probe, ix->n_cells);
+    if (ix->metric == TPQ_METRIC_COSINE) {
+      float* xn = reinterpret_cast<float*>(w + W.xnorm);
+      if (int rc = tpq_normalize_columns(x_dn, ix->d_vector, nq, xn, stream)) return rc;
+      x = xn;
+    }
+    float* probe_sims = reinterpret_cast<float*>(w + W.probe_sims);
+    int64_t* c = reinterpret_cast<int64_t*>(w + W.cells);
+    int64_t* npl = reinterpret_cast<int64_t*>(w + W.npl);
+    if (int rc = tpq_coarse_probe(x, ix->vq_codebook, ix->d_vector, nq, ix->n_cells, n_probe, smart, temperature,
+                                  probe_sims, c, npl, w + W.coarse, W.probe_sims - W.coarse, stream)) return rc;
+    cells = c; n_probe_list = npl; base_sims = probe_sims;
+  }
+  PeerOut po;
+  po.n = n_peers; po.slot = my_slot;
+  for (int p = 0; p < n_peers; ++p) { TPQ_REQUIRE(peer_keys[p], "null peer buffer"); po.keys[p] = peer_keys[p]; }
+  return scan_dispatch(ix, x, cells, n_probe_list, nq, n_probe, k, 1, reinterpret_cast<float*>(w + W.lut),
+                       reinterpret_cast<uint64_t*>(w + W.keys), (cudaStream_t)stream, base_sims, &po);
 }
 
 extern "C" int tpq_merge_topk(const uint64_t* keys_in, int nq, int n_parts, int k,

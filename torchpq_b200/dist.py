@@ -33,6 +33,51 @@ def _gather_rows(t: torch.Tensor, world: int, group):
     return out
 
 
+class PeerExchange:
+    """Gather buffers in symmetric (peer-mapped) memory for the fused scan + exchange: rank r's scan kernel stores its
+    keys straight into slot r of EVERY rank's buffer over NVLink (`tpq_ivfpq_scan_push`), a symmetric-memory barrier
+    follows, and each rank merges its own copy.  Two buffers alternate: the barrier of step i+1 orders every rank's merge
+    of step i before anybody's pushes of step i+2 into the same buffer."""
+
+    def __init__(self, group, world, nq, k, device):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        self.shape = (world, nq, k)
+        self.bufs, self.hdls, self.ptrs = [], [], []
+        for _ in range(2):
+            t = symm.empty(world, nq, k, dtype=torch.int64, device=device)
+            h = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+            self.bufs.append(t)
+            self.hdls.append(h)
+            self.ptrs.append((C.c_void_p * world)(*[int(p) for p in h.buffer_ptrs]))
+        self.step = 0
+
+    def next(self):
+        b = self.step & 1
+        self.step += 1
+        return self.bufs[b], self.hdls[b], self.ptrs[b]
+
+
+_exchanges = {}
+_p2p_broken = [False]
+
+
+def _peer_exchange(group, world, nq, k, device):
+    """One PeerExchange per (group, shape); None when symmetric memory cannot be set up here (then NCCL gathers)."""
+    if _p2p_broken[0]:
+        return None
+    key = (id(group), world, nq, k, str(device))
+    if key not in _exchanges:
+        try:
+            _exchanges[key] = PeerExchange(group, world, nq, k, device)
+        except Exception as e:                                          # no P2P mapping on this system / build
+            import warnings
+            warnings.warn(f"torchpq_b200.dist: symmetric memory unavailable ({e!r}); using the NCCL all-gather exchange")
+            _p2p_broken[0] = True
+            return None
+    return _exchanges[key]
+
+
 def make_grid(world: int, query_groups: int = 1):
     """(cell_shards, query_groups) with cell_shards * query_groups == world."""
     assert query_groups >= 1 and world % query_groups == 0, f"query_groups={query_groups} must divide world={world}"
@@ -40,7 +85,7 @@ def make_grid(world: int, query_groups: int = 1):
 
 
 def sharded_search(index, x: torch.Tensor, k: int, group=None, return_address: bool = False,
-                   split_coarse: bool = True, grid=None, coarse_group=None):
+                   split_coarse: bool = True, grid=None, coarse_group=None, exchange: str = "auto"):
     """``index`` holds this rank's shard (``dist.distribute``; or the full reference state with
     ``index.set_shard(rank % cell_shards, cell_shards)``).  Returns the same (values, ids[, address]) for the whole
     batch on every rank.
@@ -50,7 +95,12 @@ def sharded_search(index, x: torch.Tensor, k: int, group=None, return_address: b
     all-gather (2 n_probe + 1 int64 per query) hands every rank of the group the full probe lists.  Same deterministic
     kernel on every rank, so the lists are bit-identical to the replicated computation.  split_coarse=False runs the
     group's whole coarse probe on every rank: exactly one collective per batch.  ``coarse_group`` = the process group
-    of this rank's query group (needed for split_coarse when query_groups > 1; ``dist.new_group`` per group)."""
+    of this rank's query group (needed for split_coarse when query_groups > 1; ``dist.new_group`` per group).
+
+    exchange: "nccl" = scan to a local buffer, then ``all_gather_into_tensor``; "p2p" = the fused scan + exchange
+    (``PeerExchange``): the scan kernel's CTAs store their keys into every rank's gather buffer over NVLink while the
+    other CTAs are still scanning, a symmetric-memory barrier replaces the collective; "auto" = p2p on CUDA/NCCL when
+    symmetric memory can be set up and the batch is large enough not to be sliced, else nccl."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     shards, groups = grid if grid is not None else (world, 1)
@@ -64,6 +114,12 @@ def sharded_search(index, x: torch.Tensor, k: int, group=None, return_address: b
     nq, n_probe = xg.shape[1], int(index.n_probe)
     if groups > 1 and nq < per_group:                                  # ragged last group: pad so every rank gathers equal rows
         xg = torch.cat([xg, xg.new_zeros(xg.shape[0], per_group - nq)], 1)
+    ex = None
+    if world > 1 and exchange in ("auto", "p2p") and x.device.type == "cuda" and hasattr(index, "scan_push"):
+        ex = _peer_exchange(group, world, xg.shape[1], k, x.device)
+        assert ex is not None or exchange == "auto", "exchange='p2p' requested but symmetric memory is unavailable"
+    cells = base = npl = None
+    xq = xg
     if shards > 1 and split_coarse and (groups == 1 or coarse_group is not None):
         cg = group if groups == 1 else coarse_group
         xq = fn.normalize(xg.contiguous()) if index.distance == "cosine" else xg.contiguous()   # IVFPQIndex.py:474-475
@@ -73,23 +129,34 @@ def sharded_search(index, x: torch.Tensor, k: int, group=None, return_address: b
         hi = min(nqg, lo + per)
         mine = torch.zeros(per, 2 * n_probe + 1, dtype=torch.long, device=x.device)
         if hi > lo:
-            sims, cells, npl = fn.coarse_probe(xq[:, lo:hi].contiguous(), index.vq_codec.codebook, n_probe,
-                                               index.use_smart_probing, index.smart_probing_temperature)
-            mine[:hi - lo, :n_probe] = cells
-            mine[:hi - lo, n_probe] = npl
+            sims, c, n = fn.coarse_probe(xq[:, lo:hi].contiguous(), index.vq_codec.codebook, n_probe,
+                                         index.use_smart_probing, index.smart_probing_temperature)
+            mine[:hi - lo, :n_probe] = c
+            mine[:hi - lo, n_probe] = n
             mine[:hi - lo, n_probe + 1:] = sims.view(torch.int32).to(torch.long)      # fp32 bits, exact round trip
         allp = _gather_rows(mine, shards, cg)[:nqg]
         base = allp[:, n_probe + 1:].to(torch.int32).view(torch.float32).contiguous()
-        keys = index.search_cells(xq, allp[:, :n_probe].contiguous(), base_sims=base,
-                                  n_probe_list=allp[:, n_probe].contiguous(), k=k, return_keys=True)[2]
-    else:
-        keys = index.search(xg, k=k, return_keys=True)[2]
-    if world == 1:
-        keys_all = keys[None]
-    else:
-        keys_all = torch.empty((world * keys.shape[0], keys.shape[1]), dtype=keys.dtype, device=keys.device)
-        dist.all_gather_into_tensor(keys_all, keys, group=group)      # THE collective of the path: 8 B per candidate
-        keys_all = keys_all.view(world, keys.shape[0], keys.shape[1])
+        cells, npl = allp[:, :n_probe].contiguous(), allp[:, n_probe].contiguous()
+    keys_all = None
+    if ex is not None:
+        buf, hdl, ptrs = ex.next()
+        try:
+            index.scan_push(xq, k, ptrs, world, rank, cells=cells, base_sims=base, n_probe_list=npl)
+            hdl.barrier(channel=0)                                   # every rank's keys have landed in every buffer
+            keys_all = buf
+        except NotImplementedError:                                   # sliced small batch: gathered path below
+            ex.step -= 1
+    if keys_all is None:
+        if cells is not None:
+            keys = index.search_cells(xq, cells, base_sims=base, n_probe_list=npl, k=k, return_keys=True)[2]
+        else:
+            keys = index.search(xg, k=k, return_keys=True)[2]
+        if world == 1:
+            keys_all = keys[None]
+        else:
+            keys_all = torch.empty((world * keys.shape[0], keys.shape[1]), dtype=keys.dtype, device=keys.device)
+            dist.all_gather_into_tensor(keys_all, keys, group=group)      # THE collective of the path: 8 B per candidate
+            keys_all = keys_all.view(world, keys.shape[0], keys.shape[1])
     if groups == 1:
         values, ids, address = merge_gathered(keys_all, index._address2id)
     else:                                                              # rows [g*shards, (g+1)*shards) are query group g's parts

@@ -313,7 +313,26 @@ class IVFPQIndex(StateModule):
             out = out + (keys,)
         return out
 
-    # ------------------------------------------------------------------ build side (torch ops, see build.py)
+    def scan_push(self, x, k, peer_ptrs, n_peers, my_slot, cells=None, base_sims=None, n_probe_list=None):
+        """The scan of search / search_cells with its output fused into the cross-shard exchange (tpq_ivfpq_scan_push):
+        every CTA stores its top-k keys into slot `my_slot` of each rank's gather buffer (`peer_ptrs`: a ctypes array of
+        device pointers into peer-mapped memory).  Raises NotImplementedError for batches small enough to be sliced."""
+        x = self._check_query(x, k)
+        lay = self.layout()
+        dev, nq = x.device, x.shape[1]
+        n_probe = int(self.n_probe) if cells is None else cells.shape[1]
+        if cells is not None:
+            assert cells.dtype == torch.int64 and cells.shape[0] == nq and n_probe_list is not None
+            cells, n_probe_list = cells.contiguous(), n_probe_list.contiguous()
+            base_sims = base_sims.contiguous() if base_sims is not None else None
+            assert not self.pq_use_residual or base_sims is not None
+        ws_bytes = lib.tpq_search_workspace_bytes(C.byref(lay.cindex), nq, n_probe, k)
+        ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
+        check(lib.tpq_ivfpq_scan_push(C.byref(lay.cindex), ptr(x), ptr(cells), ptr(base_sims), ptr(n_probe_list), nq, n_probe, k,
+                                      int(bool(self.use_smart_probing)), float(self.smart_probing_temperature),
+                                      peer_ptrs, n_peers, my_slot, ptr(ws), ws_bytes, _lib.current_stream(dev)))
+
+    # ------------------------------------------------------------------ build side (see build.py)
     def train(self, x, force_retrain=False, seed=0):
         if self.vq_codec.is_trained and self.pq_codec.is_trained and not force_retrain:
             self.print_message("index is already trained", 1)                 # IVFPQIndex.py:235-238
