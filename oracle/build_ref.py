@@ -146,6 +146,33 @@ def build_pq_decode(tm=2, td=8, tpb=256):
     return _compile("ref_pq_decode", code + DECODE_LAUNCHER)
 
 
+PLACE_LAUNCHER = r'''
+#include <cuda_runtime.h>
+// GetIOACuda.__call__ (kernels/GetIOACuda.py:34-60): grid = ceil(n_unique / tpb); GetWriteAddressV2Cuda.__call__
+// (kernels/GetWriteAddressV2Cuda.py:33-66): grid = ceil(n_labels / tpb)
+extern "C" int ref_get_ioa_launch(const long long* labels, const long long* unique_labels, long long* ioa,
+                                  int n_labels, int n_unique, void* stream) {
+  get_ioa<<<(n_unique + %(TPB)d - 1) / %(TPB)d, %(TPB)d, 0, (cudaStream_t)stream>>>(labels, unique_labels, ioa, n_labels, n_unique);
+  return (int)cudaGetLastError();
+}
+extern "C" int ref_get_write_address_launch(const unsigned char* is_empty, const long long* div_start, const long long* div_size,
+                                            const long long* labels, const long long* ioa, long long* write_adr,
+                                            int n_slots, int n_labels, void* stream) {
+  get_write_address<<<(n_labels + %(TPB)d - 1) / %(TPB)d, %(TPB)d, 0, (cudaStream_t)stream>>>(
+      is_empty, div_start, div_size, labels, ioa, write_adr, n_slots, n_labels);
+  return (int)cudaGetLastError();
+}
+'''
+
+
+def build_placement(tpb=256):
+    """get_ioa.cu + get_write_address_v2.cu (container/CellContainer.py:89-99 constructs both with tpb=256).  The two
+    sources repeat the same typedefs, which nvcc accepts when they agree."""
+    a = open(os.path.join(REF, "get_ioa.cu")).read().replace("_TPB_", str(tpb))
+    b = open(os.path.join(REF, "get_write_address_v2.cu")).read().replace("_TPB_", str(tpb))
+    return _compile("ref_placement", a + "\n" + b + PLACE_LAUNCHER % {"TPB": tpb})
+
+
 def main():
     if not os.path.isdir(REF):
         print("oracle/_ref: /root/reference not present; keeping prebuilt files")
@@ -154,6 +181,7 @@ def main():
     outs += [build_max_sim("thread_nseuclidean", "euclidean"), build_max_sim("thread_matmul", "inner")]
     outs += [build_compute_centroids(dk) for dk in (16, 256)]
     outs += [build_pq_decode()]
+    outs += [build_placement()]
     for out in outs:
         print("built", os.path.relpath(out, HERE))
     return 0

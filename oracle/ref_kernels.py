@@ -135,3 +135,32 @@ def ivfpq_topk_residual_precomputed(data, part1, part2, cells, base_sims, cell_s
     if rc != 0:
         raise RuntimeError(f"reference kernel launch failed: cudaError {rc}")
     return values[:, :k], indices[:, :k]
+
+
+def placement_available() -> bool:
+    return os.path.exists(_so("ref_placement"))
+
+
+def get_ioa(labels):
+    """GetIOACuda.__call__ (kernels/GetIOACuda.py:34-60) on the reference kernel get_ioa.cu:8-47."""
+    lib = C.CDLL(_so("ref_placement"))
+    lib.ref_get_ioa_launch.argtypes = [C.c_void_p] * 3 + [C.c_int] * 2 + [C.c_void_p]
+    labels = labels.contiguous()
+    uniq = torch.unique(labels)
+    ioa = torch.zeros_like(labels) - 2
+    rc = lib.ref_get_ioa_launch(labels.data_ptr(), uniq.data_ptr(), ioa.data_ptr(), labels.shape[0], uniq.shape[0], _stream(labels.device))
+    assert rc == 0, rc
+    return ioa
+
+
+def get_write_address(is_empty, div_start, div_size, labels, ioa):
+    """GetWriteAddressV2Cuda.__call__ (kernels/GetWriteAddressV2Cuda.py:33-66) on get_write_address_v2.cu:9-41;
+    CellContainer.get_write_address passes (_is_empty, _cell_start, _cell_capacity, cells, ioa) (CellContainer.py:165-170)."""
+    lib = C.CDLL(_so("ref_placement"))
+    lib.ref_get_write_address_launch.argtypes = [C.c_void_p] * 6 + [C.c_int] * 2 + [C.c_void_p]
+    args = [t.contiguous() for t in (is_empty, div_start, div_size, labels, ioa)]
+    out = torch.zeros_like(labels) - 1
+    rc = lib.ref_get_write_address_launch(*[t.data_ptr() for t in args], out.data_ptr(), is_empty.shape[0], labels.shape[0],
+                                          _stream(labels.device))
+    assert rc == 0, rc
+    return out

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import ivfpq_oracle as O, build_state as B
+from oracle import ivfpq_oracle as O, build_state as B, ref_kernels as R
 
 pytestmark = pytest.mark.gpu
 
@@ -19,6 +19,8 @@ def test_get_ioa(cuda_device, n, C):
     ioa, counts = T.fn.get_ioa(torch.from_numpy(cells).cuda(), C)
     assert np.array_equal(ioa.cpu().numpy(), O.get_ioa(cells))
     assert np.array_equal(counts.cpu().numpy(), np.bincount(cells, minlength=C))
+    if R.placement_available() and n <= 20_000:                       # the reference's own get_ioa kernel (O(n * n_unique))
+        assert np.array_equal(R.get_ioa(torch.from_numpy(cells).cuda()).cpu().numpy(), ioa.cpu().numpy())
 
 
 def test_empty_prefix_and_write_address_with_holes(cuda_device):
@@ -39,6 +41,9 @@ def test_empty_prefix_and_write_address_with_holes(cuda_device):
     g = lambda a: torch.as_tensor(a).cuda()
     w = T.fn.get_write_address(g(cells), g(ioa), g(start), g(np.zeros(C, np.int64)), g(np.zeros(C, np.int64) + cap_cell),
                                T.fn.empty_prefix(g(is_empty))).cpu().numpy()
+    if R.placement_available():                                       # the reference's own get_write_address kernel
+        rw = R.get_write_address(g(is_empty), g(start), g(np.zeros(C, np.int64) + cap_cell), g(cells), g(ioa)).cpu().numpy()
+        assert np.array_equal(rw, w)
     for i in range(cells.shape[0]):                                   # the ioa-th empty slot of the cell, slot by slot
         s = start[cells[i]]
         assert w[i] == s + np.flatnonzero(is_empty[s:s + cap_cell])[ioa[i]]

@@ -98,6 +98,8 @@ __device__ __forceinline__ uint32_t box_off(int e, int c) {
   return (uint32_t)(e * 128 + ((((c >> 3) ^ (e & 3)) << 5) | ((c & 7) << 2)));
 }
 
+constexpr float kNegHuge = -3.0e38f;   // below every score; not -inf (index bits OR-ed into -inf would make a NaN)
+
 struct TcParams {
   int l, d, n, k, kpad;          // kpad = k rounded up to 32 (TMA box granularity), N of the MMA = kpad
   int tiles_per_l;               // ceil(n / 128)
@@ -252,7 +254,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
       mbar_wait(&tmem_full[tb], tph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float best = -INFINITY; int besti = 0x7fffffff;
+      float best = kNegHuge; int besti = 0;
       #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int c0 = ch * 128 + half * 64;
@@ -266,16 +268,25 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             for (int j = 0; j < 32; ++j) { P.dbg[row * 256 + c0 + j] = __uint_as_float(v0[j]); P.dbg[row * 256 + c0 + 32 + j] = __uint_as_float(v1[j]); }
           }
           const bool v1ok = c0 + 32 < P.kpad;                          // beyond kpad: stale TMEM
-          float b0 = -INFINITY, b1 = -INFINITY; int i0 = 0, i1 = 0;   // two independent chains for ILP
+          // Packed arg-max: the column index rides in the 8 low mantissa bits of the score (a perturbation of 2^-15
+          // relative, far below the TF32 rounding of the score itself), so one LOP3 + (half of) one 3-input FMNMX per
+          // column replace compare + two selects -- the arg-max warps were the kernel's issue-slot limiter (63 % busy).
+          // 255 - column: among equal truncated positive scores the lowest column wins, as before.
+          // The index embedded per column is the compile-time position inside this 64-column chunk (63 - jj: the lowest
+          // column wins among equal truncated positive scores, as before); the chunk offset is resolved once per chunk.
+          float b0 = kNegHuge, b1 = kNegHuge;                          // two independent chains for ILP
           #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s0 = __uint_as_float(v0[j]);
-            const float s1 = v1ok ? __uint_as_float(v1[j]) : -INFINITY;
-            if (s0 > b0) { b0 = s0; i0 = j; }                          // strict '>' keeps the lowest index on ties
-            if (s1 > b1) { b1 = s1; i1 = 32 + j; }
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = __uint_as_float((v0[j] & 0xFFFFFF00u) | (uint32_t)(63 - j));
+            const float p1 = __uint_as_float((v0[j + 1] & 0xFFFFFF00u) | (uint32_t)(62 - j));
+            b0 = fmaxf(fmaxf(b0, p0), p1);
+            const float q0 = __uint_as_float((v1[j] & 0xFFFFFF00u) | (uint32_t)(31 - j));
+            const float q1 = __uint_as_float((v1[j + 1] & 0xFFFFFF00u) | (uint32_t)(30 - j));
+            b1 = fmaxf(fmaxf(b1, q0), q1);
           }
-          if (b1 > b0) { b0 = b1; i0 = i1; }
-          if (b0 > best) { best = b0; besti = c0 + i0; }
+          if (!v1ok) b1 = kNegHuge;
+          const float bc = fmaxf(b0, b1);
+          if (bc > best) { best = bc; besti = c0 + 63 - (int)(__float_as_uint(bc) & 0xFFu); }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -301,21 +312,36 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const int tb = (int)(it & 1);
       if (tb == f) {
         const int s = (int)(it % TC_STAGES); const uint32_t tph = (uint32_t)(it >> 1) & 1;
-        mbar_wait(&cand_full[tb], tph);
-        float best = cand_v[(tb * 2 + 0) * 128 + row]; int besti = cand_i[(tb * 2 + 0) * 128 + row];
-        const float ov = cand_v[(tb * 2 + 1) * 128 + row]; const int oi = cand_i[(tb * 2 + 1) * 128 + row];
-        if (ov > best) { best = ov; besti = oi; }                      // halves ascend in column index: '>' keeps the lowest
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&cand_empty[tb]);
-        // exact fp32 similarity of the chosen centroid (max_sim.cu:78-98 arithmetic)
+        const uint32_t aph = (uint32_t)(it / TC_STAGES) & 1;
         // The swizzle term of box_off has period 4 in the row: four precomputed bases per operand, the row offset
         // (e * 128) folds into the load's immediate after unrolling.
         const uint8_t* xa = sA + s * (size_t)a_bytes + (row >> 5) * box_bytes;
         const uint8_t* xq[4];
         #pragma unroll
         for (int r = 0; r < 4; ++r) xq[r] = xa + box_off(r, row & 31);
+        float x2 = 0.f;
+        if (!P.exact_values) {
+          // |x|^2 as soon as the tile has LANDED (in parallel with its MMAs), then the A stage is released at once: the
+          // stage used to stay busy through MMA + arg-max + finisher (ncu: HBM 42 %, tensor pipe 48 %, the 4 x 32 KB ring
+          // covered barely one memory latency of loads in flight); now only through max(MMA, this loop).
+          mbar_wait(&full_a[s], aph);
+          #pragma unroll 2
+          for (int e4 = 0; e4 < d; e4 += 4) {
+            #pragma unroll
+            for (int r = 0; r < 4; ++r) { const float xv = *reinterpret_cast<const float*>(xq[r] + e4 * 128); x2 = fmaf(xv, xv, x2); }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_a[s]);
+        }
+        mbar_wait(&cand_full[tb], tph);
+        float best = cand_v[(tb * 2 + 0) * 128 + row]; int besti = cand_i[(tb * 2 + 0) * 128 + row];
+        const float ov = cand_v[(tb * 2 + 1) * 128 + row]; const int oi = cand_i[(tb * 2 + 1) * 128 + row];
+        if (ov > best) { best = ov; besti = oi; }                      // packed keys: the index bits break exact ties
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cand_empty[tb]);
         float acc = 0.f;
         if (P.exact_values) {
+          // exact fp32 similarity of the chosen centroid (max_sim.cu:78-98 arithmetic)
           const uint8_t* cb = sB + (besti >> 5) * box_bytes;
           const uint8_t* cq[4];
           #pragma unroll
@@ -330,23 +356,16 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               acc = fmaf(-dif, dif, acc);
             }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_a[s]);                     // this warp is done reading the A stage
         } else {
-          // -|x - c|^2 = 2 (<x,c> - |c|^2/2) - |x|^2 with the TF32 score; |x|^2 exactly, conflict-free row reads
-          float x2 = 0.f;
-          #pragma unroll 2
-          for (int e4 = 0; e4 < d; e4 += 4) {
-            #pragma unroll
-            for (int r = 0; r < 4; ++r) { const float xv = *reinterpret_cast<const float*>(xq[r] + e4 * 128); x2 = fmaf(xv, xv, x2); }
-          }
-          acc = fmaf(2.f, best, -x2);
+          acc = fmaf(2.f, best, -x2);                                  // -|x - c|^2 = 2 (<x,c> - |c|^2/2) - |x|^2 with the TF32 score
         }
         const long long p = (long long)ti * TC_M + row;
         if (p < P.n) {
           P.maxsims[(size_t)li * P.n + p] = acc;
           P.labels[(size_t)li * P.n + p] = besti;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_a[s]);                       // this warp is done reading the A stage
       }
       if (last_of_l) {
         __syncwarp();
