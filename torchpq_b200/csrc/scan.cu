@@ -581,6 +581,9 @@ static int fused_dsub(const tpq_index* ix) {
 #endif
   // residual IVFPQ keeps TWO tables when the query half is built in the CTA: that fits for M <= 64 and pays for d/M <= 4
   if (ix->residual && (ix->m_pad > 64 || dsub == 8)) return 0;
+#ifdef TPQ_DEBUG_KNOBS
+  { const char* rm = getenv("TPQ_RES_MODE"); if (ix->residual && rm && !strncmp(rm, "staged", 6)) return 0; }
+#endif
   return (dsub == 1 || dsub == 2 || dsub == 4 || dsub == 8) ? dsub : 0;
 }
 
@@ -691,6 +694,13 @@ static int scan_dispatch(const tpq_index* ix, const float* x, const int64_t* cel
     if (!ix->part2_scan || !base_sims) { set_error("residual search needs part2_scan and base_sims"); return TPQ_ERR_BAD_ARG; }
     if (ix->metric != TPQ_METRIC_EUCLIDEAN) { set_error("residual IVFPQ is defined for the euclidean metric"); return TPQ_ERR_UNSUPPORTED; }
 #define TPQ_RES(MPv, DS) launch_scan_d<MPv, 16, 1, DS, true>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, base_sims, peers)
+#ifdef TPQ_DEBUG_KNOBS
+    { const char* rm = getenv("TPQ_RES_MODE");                      // A/B: staged query half + 3 light CTAs/SM for M <= 64
+      if (rm && !strcmp(rm, "staged3") && ix->m_pad == 64)
+        return launch_scan_d<64, 8, 3, 0, true>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, base_sims, peers);
+      if (rm && !strcmp(rm, "staged2") && ix->m_pad == 64)
+        return launch_scan_d<64, 8, 2, 0, true>(ix, x, cells, npl, nq, n_probe, k, S, lut_ws, keys, st, base_sims, peers); }
+#endif
     switch (fused_dsub(ix)) {
       case 1: return ix->m_pad == 32 ? TPQ_RES(32, 1) : TPQ_RES(64, 1);
       case 2: return ix->m_pad == 32 ? TPQ_RES(32, 2) : TPQ_RES(64, 2);
