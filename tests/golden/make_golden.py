@@ -56,5 +56,47 @@ def main(out_dir):
         print(name, "rows", nq, "tie-free", int(tie_free.sum()))
 
 
+def residual_and_placement(out_dir):
+    """Round 2: golden vectors from the reference's `ivfpq_topk_residual_precomputed` kernel (ivfpq_topk.cu:1039-1207)
+    and from its placement kernels get_ioa.cu / get_write_address_v2.cu."""
+    g = lambda a: torch.as_tensor(a).cuda()
+    for name, M, d, C, n, n_probe, k, nq, smart in [("res_m16", 16, 64, 16, 4000, 6, 20, 24, True),
+                                                     ("res_m64", 64, 128, 16, 3000, 5, 50, 12, False)]:
+        torch.manual_seed(len(name) + M)
+        st = B.build_state_residual(torch.randn(d, n), M, C, vq_iters=2, pq_iters=1)
+        st.n_probe, st.use_smart_probing = n_probe, smart
+        x = torch.randn(d, nq)
+        xx, sims, cells, npl = O.coarse_probe(st, x)
+        p1, p2 = O.residual_parts(xx, torch.from_numpy(st.vq_codebook), torch.from_numpy(st.pq_codebook))
+        cn = cells.numpy()
+        cs, cz = st.cell_start[cn], st.cell_size[cn]
+        rv, ra = R.ivfpq_topk_residual_precomputed(g(st.storage), p1.cuda(), p2.cuda(), cells.cuda(), sims.cuda(), g(cs), g(cz),
+                                                   g(st.is_empty), npl.cuda(), k)
+        rv1, _ = R.ivfpq_topk_residual_precomputed(g(st.storage), p1.cuda(), p2.cuda(), cells.cuda(), sims.cuda(), g(cs), g(cz),
+                                                   g(st.is_empty), npl.cuda(), k + 1)
+        rv, ra, rv1 = rv.cpu().numpy(), ra.cpu().numpy(), rv1.cpu().numpy()
+        tie_free = np.all(np.diff(rv1, axis=1) != 0, axis=1)
+        np.savez_compressed(os.path.join(out_dir, f"residual_{name}.npz"), storage=st.storage, part1=p1.numpy(), part2=p2.numpy(),
+                            cells=cn, base_sims=sims.numpy(), is_empty=st.is_empty, cell_start=cs, cell_size=cz,
+                            n_probe_list=npl.numpy(), k=np.int64(k), ref_values=rv, ref_address=ra, tie_free=tie_free)
+        print("residual", name, "tie-free", int(tie_free.sum()))
+    rng = np.random.default_rng(12)
+    C, cap_cell, n = 23, 97, 900
+    is_empty = (rng.random(C * cap_cell) < 0.55).astype(np.uint8)
+    start = np.arange(C, dtype=np.int64) * cap_cell
+    free = np.array([int(is_empty[s:s + cap_cell].sum()) for s in start], dtype=np.int64)
+    cells = np.repeat(np.arange(C), np.minimum(free, rng.integers(5, 60, C)))
+    rng.shuffle(cells)
+    ioa = R.get_ioa(g(cells))
+    w = R.get_write_address(g(is_empty), g(start), g(np.zeros(C, np.int64) + cap_cell), g(cells), ioa)
+    np.savez_compressed(os.path.join(out_dir, "placement.npz"), cells=cells, is_empty=is_empty, cell_start=start,
+                        cell_capacity=np.zeros(C, np.int64) + cap_cell, ref_ioa=ioa.cpu().numpy(), ref_write_address=w.cpu().numpy())
+    print("placement", cells.shape[0], "items")
+
+
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))
+    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
+    if "--round2-only" not in sys.argv:
+        main(out)
+    os.makedirs(out, exist_ok=True)
+    residual_and_placement(out)
