@@ -317,3 +317,31 @@ def test_wide_codes_unit_pipeline(cuda_device, M, d):
     ix = make_index(st)
     v, i, a = ix.search(x.cuda(), k=50, return_address=True)
     assert np.array_equal(v.cpu().numpy(), ov) and np.array_equal(a.cpu().numpy(), oa) and np.array_equal(i.cpu().numpy(), oi)
+
+
+def test_scan_push_single_gpu(cuda_device):
+    """tpq_ivfpq_scan_push (the fused scan + exchange of dist.sharded_search) with this GPU as its only 'peer': the keys
+    each CTA pushes into slot 0 of the gather buffer are exactly the keys search() returns, for both the in-kernel coarse
+    probe and caller-supplied probe lists; a batch small enough to be sliced is refused (the caller then gathers)."""
+    import ctypes as C
+    import torchpq_b200 as T
+    st, queries = B.integer_state(64, 16, 32, 20000, seed=31, lo=-6, hi=7)
+    st.n_probe, st.use_smart_probing = 8, True
+    ix = make_index(st)
+    x = queries(700).cuda()                                       # >= 592 queries: one CTA per query, no slices
+    k = 50
+    v, i, keys = ix.search(x, k=k, return_keys=True)
+    buf = torch.zeros(1, 700, k, dtype=torch.int64, device="cuda")
+    ptrs = (C.c_void_p * 1)(buf.data_ptr())
+    ix.scan_push(x, k, ptrs, 1, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(buf[0], keys)
+    sims, cells, npl = T.fn.coarse_probe(x, ix.vq_codec.codebook, 8, True, 30.0)
+    buf.zero_()
+    ix.scan_push(x, k, ptrs, 1, 0, cells=cells, base_sims=sims, n_probe_list=npl)
+    torch.cuda.synchronize()
+    assert torch.equal(buf[0], keys)
+    v2, i2, a2 = T.fn.merge_topk(buf, ix._address2id)
+    assert torch.equal(v2, v) and torch.equal(i2, i)
+    with pytest.raises(NotImplementedError):
+        ix.scan_push(x[:, :40].contiguous(), k, ptrs, 1, 0)
