@@ -100,6 +100,13 @@ __device__ __forceinline__ uint32_t box_off(int e, int c) {
 
 constexpr float kNegHuge = -3.0e38f;   // below every score; not -inf (index bits OR-ed into -inf would make a NaN)
 
+#ifdef TPQ_DEBUG_KNOBS
+#define TC_WAIT(slot, bar, par) do { const long long t0__ = clock64(); mbar_wait(bar, par); \
+    if (P.wait && (threadIdx.x & 31) == 0) atomicAdd(P.wait + (slot), (unsigned long long)(clock64() - t0__)); } while (0)
+#else
+#define TC_WAIT(slot, bar, par) mbar_wait(bar, par)
+#endif
+
 struct TcParams {
   int l, d, n, k, kpad;          // kpad = k rounded up to 32 (TMA box granularity), N of the MMA = kpad
   int tiles_per_l;               // ceil(n / 128)
@@ -107,8 +114,10 @@ struct TcParams {
   const float* cent;             // for |c|^2 of padded columns nothing is read: TMA zero-fills
   float* dbg;                    // debug: raw accumulators of tile 0 of CTA 0, [128][256]
   int exact_values;              // 1: maxsims recomputed exactly in fp32 for the chosen centroid; 0: 2*score - |x|^2 from the TF32 score
+  unsigned long long* wait;      // debug build: summed wait cycles per barrier kind [8], [7] = total CTA cycles
 };
 static float* g_tc_dbg = nullptr;
+static unsigned long long* g_tc_wait = nullptr;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c, TcParams P) {
@@ -137,9 +146,16 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   int* cand_i = reinterpret_cast<int*>(cand_v + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef TPQ_DEBUG_KNOBS
+  const long long t_cta0 = clock64();
+#endif
   const long long total_tiles = (long long)P.l * P.tiles_per_l;
+  // Contiguous tile range per CTA (one or two centroid-tile loads per CTA).  A round-robin deal (adjacent strips across
+  // the grid, for DRAM page locality) was measured: 4.99 vs 4.70 ms -- the per-k-means reload of the centroid tile costs
+  // more than the locality buys.
   const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
   const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
+  const long long t_step = 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_x) : "memory");
@@ -172,7 +188,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     if (lane == 0) {
       int cur_l = -1; uint32_t bgen = 0;
       long long it = 0;
-      for (long long t = t_begin; t < t_end; ++t, ++it) {
+      for (long long t = t_begin; t < t_end; t += t_step, ++it) {
         const int li = (int)(t / P.tiles_per_l), ti = (int)(t % P.tiles_per_l);
         if (li != cur_l) {
           if (cur_l >= 0) { mbar_wait(b_free, bgen & 1); ++bgen; }     // every MMA + epilogue read of the old B is done
@@ -181,7 +197,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           cur_l = li;
         }
         const int s = (int)(it % TC_STAGES); const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1;
-        mbar_wait(&empty_a[s], ph ^ 1);
+        TC_WAIT(0, &empty_a[s], ph ^ 1);
         mbar_expect_tx(&full_a[s], a_bytes);
         for (int g = 0; g < 4; ++g) tma_load_3d(sA + s * a_bytes + g * box_bytes, &map_x, &full_a[s], ti * TC_M + g * 32, 0, li);
       }
@@ -194,13 +210,13 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                            ((uint32_t)(P.kpad >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     int cur_l = -1; uint32_t bgen = 0;
     long long it = 0;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
+    for (long long t = t_begin; t < t_end; t += t_step, ++it) {
       const int li = (int)(t / P.tiles_per_l);
       if (li != cur_l) { mbar_wait(b_full, bgen & 1); mbar_wait(c2_ready, bgen & 1); ++bgen; cur_l = li; }
       const int s = (int)(it % TC_STAGES); const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1;
       const int tb = (int)(it & 1); const uint32_t tph = (uint32_t)(it >> 1) & 1;
-      mbar_wait(&tmem_empty[tb], tph ^ 1);
-      mbar_wait(&full_a[s], ph);
+      TC_WAIT(1, &tmem_empty[tb], tph ^ 1);
+      TC_WAIT(2, &full_a[s], ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
         const uint32_t a0 = smem_u32(sA + s * a_bytes), b0 = smem_u32(sB);
@@ -213,7 +229,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         umma_tf32(tmem_base + tb * 256, umma_desc(smem_u32(sAx), 1024, 512), umma_desc(smem_u32(sBx), 1024, 512), idesc, 1u);
         umma_commit(&empty_a[s]);                                      // MMA done with this A stage
         umma_commit(&tmem_full[tb]);                                   // accumulator ready
-        const bool last_of_l = (t + 1 == t_end) || ((int)((t + 1) / P.tiles_per_l) != li);
+        const bool last_of_l = (t + t_step >= t_end) || ((int)((t + t_step) / P.tiles_per_l) != li);
         if (last_of_l) umma_commit(b_free);
       }
       __syncwarp();
@@ -228,7 +244,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int at = threadIdx.x - 64;                                   // 0..255 among arg-max threads = centroid column
     int cur_l = -1; uint32_t bgen = 0;
     long long it = 0;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
+    for (long long t = t_begin; t < t_end; t += t_step, ++it) {
       const int li = (int)(t / P.tiles_per_l);
       const int tb = (int)(it & 1); const uint32_t tph = (uint32_t)(it >> 1) & 1;
       if (li != cur_l) {
@@ -252,7 +268,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(c2_ready);
       }
-      mbar_wait(&tmem_full[tb], tph);
+      TC_WAIT(3, &tmem_full[tb], tph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float best = kNegHuge; int besti = 0;
       #pragma unroll
@@ -292,7 +308,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[tb]);
-      mbar_wait(&cand_empty[tb], tph ^ 1);                             // finishers are done with this candidate buffer
+      TC_WAIT(4, &cand_empty[tb], tph ^ 1);                            // finishers are done with this candidate buffer
       cand_v[(tb * 2 + ch) * 128 + row] = best;
       cand_i[(tb * 2 + ch) * 128 + row] = besti;
       __syncwarp();
@@ -305,9 +321,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int row = ((warp - 10) & 3) * 32 + lane;
     int cur_l = -1; uint32_t bgen = 0;
     long long it = 0;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
+    for (long long t = t_begin; t < t_end; t += t_step, ++it) {
       const int li = (int)(t / P.tiles_per_l), ti = (int)(t % P.tiles_per_l);
-      const bool last_of_l = (t + 1 == t_end) || ((int)((t + 1) / P.tiles_per_l) != li);
+      const bool last_of_l = (t + t_step >= t_end) || ((int)((t + t_step) / P.tiles_per_l) != li);
       if (li != cur_l) { mbar_wait(b_full, bgen & 1); ++bgen; cur_l = li; }   // B tile of this k-means is in shared memory
       const int tb = (int)(it & 1);
       if (tb == f) {
@@ -324,7 +340,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           // |x|^2 as soon as the tile has LANDED (in parallel with its MMAs), then the A stage is released at once: the
           // stage used to stay busy through MMA + arg-max + finisher (ncu: HBM 42 %, tensor pipe 48 %, the 4 x 32 KB ring
           // covered barely one memory latency of loads in flight); now only through max(MMA, this loop).
-          mbar_wait(&full_a[s], aph);
+          TC_WAIT(5, &full_a[s], aph);
           #pragma unroll 2
           for (int e4 = 0; e4 < d; e4 += 4) {
             #pragma unroll
@@ -333,7 +349,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty_a[s]);
         }
-        mbar_wait(&cand_full[tb], tph);
+        TC_WAIT(6, &cand_full[tb], tph);
         float best = cand_v[(tb * 2 + 0) * 128 + row]; int besti = cand_i[(tb * 2 + 0) * 128 + row];
         const float ov = cand_v[(tb * 2 + 1) * 128 + row]; const int oi = cand_i[(tb * 2 + 1) * 128 + row];
         if (ov > best) { best = ov; besti = oi; }                      // packed keys: the index bits break exact ties
@@ -373,6 +389,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
     }
   }
+#ifdef TPQ_DEBUG_KNOBS
+  if (P.wait && threadIdx.x == 0) atomicAdd(P.wait + 7, (unsigned long long)(clock64() - t_cta0));
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -426,6 +445,7 @@ int launch_assign_tc(const float* data, const float* cent, int l, int d, long lo
   P.l = l; P.d = d; P.n = (int)n; P.k = k; P.kpad = (k + 31) / 32 * 32;
   P.tiles_per_l = (int)((n + TC_M - 1) / TC_M);
   P.maxsims = maxsims; P.labels = labels; P.cent = cent; P.dbg = g_tc_dbg; P.exact_values = exact_values;
+  P.wait = g_tc_wait;
   const size_t box = (size_t)d * 128;
   const size_t smem = (size_t)(P.kpad / 32) * box + (size_t)TC_STAGES * 4 * box + 12 * 1024 + 256 * 4 + 32 * 8 + 8192 + 1024;
   TPQ_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -442,3 +462,4 @@ int launch_assign_tc(const float* data, const float* cent, int l, int d, long lo
 }  // namespace tpq
 
 extern "C" void tpq_debug_set_tc_dump(float* p) { tpq::g_tc_dbg = p; }
+extern "C" void tpq_debug_set_tc_wait(unsigned long long* p) { tpq::g_tc_wait = p; }
