@@ -599,6 +599,8 @@ def main():
                     help="multi-GPU grid: ranks = cell_shards x query_groups (0 = auto: 1 up to 4 GPUs, 2 at 8)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU key exchange: fused scan + P2P push into symmetric memory (auto/p2p) or NCCL all-gather")
+    ap.add_argument("--no-split-coarse", action="store_true",
+                    help="multi-GPU: every rank runs its query group's whole coarse probe (no probe-list all-gather)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary block (c2/c4/c3c/C5/build/reference kernel)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -621,6 +623,7 @@ def main():
     config = {"workload": f"{args.workload}: {desc}", "n_query_per_step": args.nq,
               "index_sharding": f"cells mod {shards}" + (f" x {groups} query groups" if groups > 1 else ""),
               "use_smart_probing": not args.no_smart,
+              "coarse_probe": ("replicated per query group" if args.no_split_coarse else "split by queries inside a query group + all-gather of probe lists") if world > 1 else "single GPU",
               "exchange": ("fused scan + P2P key push (symmetric memory) + barrier" if args.exchange != "nccl" else "NCCL all-gather") if world > 1 else "none",
               "l2_policy": "inputs larger than L2 (code store >= 640 MB vs 126 MB L2; 4 rotating query batches)",
               "training": f"seeded k-means, <= {VQ_ITERS} (coarse) / {PQ_ITERS} (PQ) Lloyd iterations, tol 1e-4 (the reference's settings)"}
@@ -681,7 +684,8 @@ def main():
 
     def search(x):
         if world > 1:
-            return tdist.sharded_search(index, x, k, grid=grid, coarse_group=coarse_group, exchange=args.exchange)
+            return tdist.sharded_search(index, x, k, grid=grid, coarse_group=coarse_group, exchange=args.exchange,
+                                        split_coarse=not args.no_split_coarse)
         return index.search(x, k=k)
 
     def step_device(i):
