@@ -599,6 +599,9 @@ def main():
                     help="multi-GPU grid: ranks = cell_shards x query_groups (0 = auto: 1 up to 4 GPUs, 2 at 8)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU key exchange: fused scan + P2P push into symmetric memory (auto/p2p) or NCCL all-gather")
+    ap.add_argument("--pipeline", type=int, default=2,
+                    help="streams the timed loops alternate over: step i+1's probe/scan overlaps step i's exchange, merge "
+                         "and tail (1 = strictly serial steps)")
     ap.add_argument("--no-split-coarse", action="store_true",
                     help="multi-GPU: every rank runs its query group's whole coarse probe (no probe-list all-gather)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary block (c2/c4/c3c/C5/build/reference kernel)")
@@ -622,7 +625,7 @@ def main():
     shards = world // groups
     config = {"workload": f"{args.workload}: {desc}", "n_query_per_step": args.nq,
               "index_sharding": f"cells mod {shards}" + (f" x {groups} query groups" if groups > 1 else ""),
-              "use_smart_probing": not args.no_smart,
+              "use_smart_probing": not args.no_smart, "pipeline_streams": max(1, args.pipeline),
               "coarse_probe": ("replicated per query group" if args.no_split_coarse else "split by queries inside a query group + all-gather of probe lists") if world > 1 else "single GPU",
               "exchange": ("fused scan + P2P key push (symmetric memory) + barrier" if args.exchange != "nccl" else "NCCL all-gather") if world > 1 else "none",
               "l2_policy": "inputs larger than L2 (code store >= 640 MB vs 126 MB L2; 4 rotating query batches)",
@@ -688,40 +691,50 @@ def main():
                                         split_coarse=not args.no_split_coarse)
         return index.search(x, k=k)
 
+    # Steps are independent batches, so consecutive steps alternate over `--pipeline` streams: step i+1's coarse probe and
+    # the head of its scan run while step i's exchange barrier, merge and last scan wave finish (all inside the timed
+    # region; the roofline leg below times strictly serial steps).
+    n_pipe = max(1, args.pipeline)
+    pipe = [torch.cuda.Stream(device) for _ in range(n_pipe)] if n_pipe > 1 else [torch.cuda.current_stream(device)]
+
     def step_device(i):
+        with torch.cuda.stream(pipe[i % n_pipe]):
+            return search(xs_dev[i % len(xs_dev)])
+
+    def step_serial(i):
         return search(xs_dev[i % len(xs_dev)])
 
     # end-to-end leg: host (pinned) queries in, host (pinned) results out, every step.  H2D and D2H run on their own
-    # streams with double-buffered staging tensors, so step i's D2H and step i+1's H2D overlap the searches -- all of it
+    # streams with staging tensors per pipeline slot, so step i's D2H and step i+1's H2D overlap the searches -- all of it
     # inside the timed region.  (Round 1 used ONE copy stream: H2D i+1 then queued behind D2H i, which waits for search
     # i, so every step paid search + D2H + H2D in series -- 1.07 ms of the 2.88 ms e2e step at 8 GPUs.)
     h2d_stream, d2h_stream = torch.cuda.Stream(device), torch.cuda.Stream(device)
-    out_v = [torch.empty(nq, k, dtype=torch.float32).pin_memory() for _ in range(2)]
-    out_i = [torch.empty(nq, k, dtype=torch.long).pin_memory() for _ in range(2)]
-    x_in = [torch.empty(d, nq, dtype=torch.float32, device=device) for _ in range(2)]
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
-    res = [None, None]
+    n_slot = 2 * n_pipe
+    out_v = [torch.empty(nq, k, dtype=torch.float32).pin_memory() for _ in range(n_slot)]
+    out_i = [torch.empty(nq, k, dtype=torch.long).pin_memory() for _ in range(n_slot)]
+    x_in = [torch.empty(d, nq, dtype=torch.float32, device=device) for _ in range(n_slot)]
+    ev_in = [torch.cuda.Event() for _ in range(n_slot)]
+    ev_done = [torch.cuda.Event() for _ in range(n_slot)]
+    ev_free = [torch.cuda.Event() for _ in range(n_slot)]
+    res = [None] * n_slot
 
     def step_e2e(i):
-        b = i & 1
-        main = torch.cuda.current_stream(device)
+        b = i % n_slot
+        main = pipe[i % n_pipe]
         with torch.cuda.stream(h2d_stream):
-            h2d_stream.wait_event(ev_free[b])                        # search i-2 no longer reads x_in[b]
+            h2d_stream.wait_event(ev_free[b])                        # the search that last used x_in[b] has read it
             x_in[b].copy_(xs_host[i % len(xs_host)], non_blocking=True)
             ev_in[b].record(h2d_stream)
-        main.wait_event(ev_in[b])
-        v, ids = search(x_in[b])
-        ev_free[b].record(main)
-        ev_done[b].record(main)
+        with torch.cuda.stream(main):
+            main.wait_event(ev_in[b])
+            v, ids = search(x_in[b])
+            ev_free[b].record(main)
+            ev_done[b].record(main)
         res[b] = (v, ids)                                            # keep alive until the copy stream has read them
         with torch.cuda.stream(d2h_stream):
             d2h_stream.wait_event(ev_done[b])
             out_v[b].copy_(v, non_blocking=True); out_i[b].copy_(ids, non_blocking=True)
             v.record_stream(d2h_stream); ids.record_stream(d2h_stream)
-            ev_out[b].record(d2h_stream)
 
     def barrier():
         if world > 1:
@@ -730,13 +743,15 @@ def main():
 
     def timed(fn, steps):
         barrier()
+        cur = torch.cuda.current_stream(device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        for st in pipe + [h2d_stream, d2h_stream]:
+            st.wait_event(e0)                                        # nothing of the timed work starts before e0
         for i in range(steps):
             fn(i)
-        if fn is step_e2e:
-            torch.cuda.current_stream(device).wait_stream(d2h_stream)
-            torch.cuda.current_stream(device).wait_stream(h2d_stream)
+        for st in pipe + [h2d_stream, d2h_stream]:
+            cur.wait_stream(st)                                      # ... and all of it ends before e1
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
@@ -745,11 +760,12 @@ def main():
         return float(ms.item())
 
     sampler = ClockSampler(local_rank) if rank == 0 else None      # samples across warm-up and both timed regions
-    for i in range(args.warmup):
-        step_device(i); step_e2e(i)
-    scan_profile_begin()                                          # events around every scan launch of the TIMED device loop
-    ms_dev = timed(step_device, args.steps)
+    for i in range(max(args.warmup, 2 * n_pipe)):                   # every pipeline slot warmed (symmetric-memory set-up included)
+        step_device(i); step_e2e(i); step_serial(i)
+    scan_profile_begin()                                          # roofline leg: K steps strictly one after the other,
+    ms_serial = timed(step_serial, args.steps)                    # CUDA events around every scan launch (tpq_profile_*)
     scan_ms_total, scan_launches = scan_profile_end()
+    ms_dev = timed(step_device, args.steps)
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
     qps = nq * args.steps / (ms_dev / 1e3)
@@ -830,9 +846,11 @@ def main():
                      "frac": (ach / peak) if ach else None, "traffic": profiled_traffic(args.workload, world), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": rf["algorithmic_bytes_per_launch"],
                      "scan_ms_per_launch": rf["scan_ms_per_launch"],
-                     "scan_share_of_step": rf["scan_ms_per_launch"] / (ms_dev / args.steps),
+                     "serial_ms_per_step": ms_serial / args.steps,
+                     "scan_share_of_step": rf["scan_ms_per_launch"] / (ms_serial / args.steps),
                      "mean_probes_scanned": rf["mean_probes_scanned"], "rank": 0, "launches_timed": rf["launches"],
-                     "timed_in": "the timed device loop itself (CUDA events around every scan launch, same clocks as `value`)"},
+                     "timed_in": "a third timed loop of the same K steps run strictly serially (CUDA events around every scan launch); "
+                                 "`value` and `e2e` alternate steps over `config.pipeline_streams` streams"},
         "cpu_baseline": cpu, "clocks": clocks, "secondary": secondary,
     }
     print(json.dumps(line), flush=True)

@@ -66,7 +66,9 @@ def _peer_exchange(group, world, nq, k, device):
     """One PeerExchange per (group, shape); None when symmetric memory cannot be set up here (then NCCL gathers)."""
     if _p2p_broken[0]:
         return None
-    key = (id(group), world, nq, k, str(device))
+    # one pair of buffers per STREAM: callers that pipeline batches over several streams (bench.py) must not share them
+    # (the reuse argument above orders steps of one stream only)
+    key = (id(group), world, nq, k, str(device), torch.cuda.current_stream(device).cuda_stream)
     if key not in _exchanges:
         try:
             _exchanges[key] = PeerExchange(group, world, nq, k, device)
