@@ -602,8 +602,11 @@ def main():
     ap.add_argument("--pipeline", type=int, default=2,
                     help="streams the timed loops alternate over: step i+1's probe/scan overlaps step i's exchange, merge "
                          "and tail (1 = strictly serial steps)")
-    ap.add_argument("--no-split-coarse", action="store_true",
-                    help="multi-GPU: every rank runs its query group's whole coarse probe (no probe-list all-gather)")
+    ap.add_argument("--split-coarse", default="auto", choices=["auto", "on", "off"],
+                    help="multi-GPU coarse probe: split by queries inside a query group + all-gather of the probe lists (on), or "
+                         "replicated per query group (off); auto = on without query groups, off with them (measured at 8 GPUs, "
+                         "4 x 2: on 6.02 M device / 4.67 M e2e q/s, off 5.84 M / 5.26 M -- the extra collective and its host-side "
+                         "packing cost the end-to-end loop more than the replicated 5000-query probe costs the device)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary block (c2/c4/c3c/C5/build/reference kernel)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -623,10 +626,11 @@ def main():
     if world % groups:
         groups = 1
     shards = world // groups
+    split_coarse = (groups == 1) if args.split_coarse == "auto" else (args.split_coarse == "on")
     config = {"workload": f"{args.workload}: {desc}", "n_query_per_step": args.nq,
               "index_sharding": f"cells mod {shards}" + (f" x {groups} query groups" if groups > 1 else ""),
               "use_smart_probing": not args.no_smart, "pipeline_streams": max(1, args.pipeline),
-              "coarse_probe": ("replicated per query group" if args.no_split_coarse else "split by queries inside a query group + all-gather of probe lists") if world > 1 else "single GPU",
+              "coarse_probe": ("replicated per query group" if not split_coarse else "split by queries inside a query group + all-gather of probe lists") if world > 1 else "single GPU",
               "exchange": ("fused scan + P2P key push (symmetric memory) + barrier" if args.exchange != "nccl" else "NCCL all-gather") if world > 1 else "none",
               "l2_policy": "inputs larger than L2 (code store >= 640 MB vs 126 MB L2; 4 rotating query batches)",
               "training": f"seeded k-means, <= {VQ_ITERS} (coarse) / {PQ_ITERS} (PQ) Lloyd iterations, tol 1e-4 (the reference's settings)"}
@@ -688,7 +692,7 @@ def main():
     def search(x):
         if world > 1:
             return tdist.sharded_search(index, x, k, grid=grid, coarse_group=coarse_group, exchange=args.exchange,
-                                        split_coarse=not args.no_split_coarse)
+                                        split_coarse=split_coarse)
         return index.search(x, k=k)
 
     # Steps are independent batches, so consecutive steps alternate over `--pipeline` streams: step i+1's coarse probe and
