@@ -643,7 +643,7 @@ static int launch_scan_d(const tpq_index* ix, const float* x, const int64_t* cel
 #ifdef TPQ_DEBUG_KNOBS
     { const char* br = getenv("TPQ_BOOT_R"); if (br && atoi(br) == 1) A.boot_r = 1; }
     A.phase = g_phase;
-    { const char* bm = getenv("TPQ_BOOT_MODE"); A.boot_mode = bm ? atoi(bm) : 0; }
+    { const char* bm = getenv("TPQ_BOOT_MODE"); A.boot_mode = bm ? atoi(bm) : 1; }
 #endif
     const bool prof = g_prof_on && g_prof_n < kProfMax;
     if (prof) cudaEventRecord(g_prof_start[g_prof_n], st);
