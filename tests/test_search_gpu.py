@@ -345,3 +345,19 @@ def test_scan_push_single_gpu(cuda_device):
     assert torch.equal(v2, v) and torch.equal(i2, i)
     with pytest.raises(NotImplementedError):
         ix.scan_push(x[:, :40].contiguous(), k, ptrs, 1, 0)
+
+
+def test_drop_reference_layout(cuda_device):
+    """A search-only index: after drop_reference_layout() the reference-layout code store is gone, results are unchanged."""
+    st, queries = B.integer_state(64, 16, 32, 20000, seed=33, lo=-6, hi=7)
+    st.n_probe, st.use_smart_probing = 8, True
+    ix = make_index(st)
+    x = queries(50).cuda()
+    v0, i0 = ix.search(x, k=20)
+    before = ix.resident_bytes()
+    ix.drop_reference_layout()
+    assert ix._storage is None and ix._is_empty is None and ix.resident_bytes() < before
+    v1, i1 = ix.search(x, k=20)
+    assert torch.equal(v0, v1) and torch.equal(i0, i1)
+    with pytest.raises(AssertionError):
+        ix.add(queries(5).cuda())

@@ -196,6 +196,7 @@ def container_add(index, codes: torch.Tensor, cells: torch.Tensor, ids=None, ret
 def add(index, x: torch.Tensor, ids=None, return_address=False, chunk: int = 1 << 20):
     """IVFPQIndex.add: encode x [d, n] and store it."""
     assert x.dim() == 2 and x.shape[0] == index.d_vector
+    assert index._storage is not None, "shard-only / search-only index: add to the full index (reload the checkpoint)"
     from . import fn
     cells_l, codes_l = [], []
     for s in range(0, x.shape[1], chunk):

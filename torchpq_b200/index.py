@@ -231,6 +231,12 @@ class IVFPQIndex(StateModule):
         self._layout = ScanLayout(self, shard_rank, shard_world, parts=(codes_scan, block_valid, cell_block_start, n_blocks))
         return self
 
+    def drop_reference_layout(self):
+        """Search-only deployment on one GPU: keep the scan layout, free `_storage` / `_is_empty` (C3: 0.8 GB of the 1.8 GB
+        the index holds).  The index becomes shard-only (shard 0 of 1): add / remove need a reload of the checkpoint."""
+        lay = self.layout()
+        return self.adopt_shard(lay.shard[0], lay.shard[1], lay.codes_scan, lay.block_valid, lay.cell_block_start, lay.n_blocks)
+
     def resident_bytes(self) -> int:
         """Device bytes this index object holds (registered buffers, codebooks, scan layout)."""
         n = sum(t.numel() * t.element_size() for t in self.buffers() if t is not None)
