@@ -21,7 +21,7 @@ constexpr int PL_CH = 4096;          // labels per chunk (one CTA)
 // hist[chunk][label] (dense, zeroed by the caller), local ranks to lrank[i].
 __global__ void __launch_bounds__(512)
 ioa_local_kernel(const int64_t* __restrict__ cells, int64_t n, int n_cells, uint16_t* __restrict__ lrank,
-                 int32_t* __restrict__ hist, int* __restrict__ bad) {
+                 int32_t* __restrict__ hist) {
   __shared__ uint64_t key[PL_CH];
   const int64_t base = (int64_t)blockIdx.x * PL_CH;
   const int np = (int)min((int64_t)PL_CH, n - base);
@@ -29,8 +29,7 @@ ioa_local_kernel(const int64_t* __restrict__ cells, int64_t n, int n_cells, uint
     uint64_t kk = ~0ull;                                              // padding sorts last
     if (i < np) {
       const int64_t c = cells[base + i];
-      if (c < 0 || c >= n_cells) { *bad = 1; }
-      else kk = ((uint64_t)c << 32) | (uint32_t)i;
+      if (c >= 0 && c < n_cells) kk = ((uint64_t)c << 32) | (uint32_t)i;   // out-of-range labels are left out (ioa 0, not counted)
     }
     key[i] = kk;
   }
@@ -236,7 +235,7 @@ static inline int64_t n_chunks_of(int64_t n) { return (n + PL_CH - 1) / PL_CH; }
 
 extern "C" size_t tpq_ioa_workspace_bytes(int64_t n, int n_cells) {
   if (n <= 0 || n_cells <= 0) return 0;
-  return align_up((size_t)n_chunks_of(n) * n_cells * 4, 256) + align_up((size_t)n * 2, 256) + 256;
+  return align_up((size_t)n_chunks_of(n) * n_cells * 4, 256) + align_up((size_t)n * 2, 256);
 }
 
 extern "C" int tpq_get_ioa(const int64_t* cells, int64_t n, int n_cells, int64_t* ioa, int64_t* counts,
@@ -250,11 +249,9 @@ extern "C" int tpq_get_ioa(const int64_t* cells, int64_t n, int n_cells, int64_t
   TPQ_REQUIRE(nch <= 0x7fffffff, "tpq_get_ioa: too many items for one call");
   uint8_t* w = reinterpret_cast<uint8_t*>(ws);
   int32_t* hist = reinterpret_cast<int32_t*>(w);            w += align_up((size_t)nch * n_cells * 4, 256);
-  uint16_t* lrank = reinterpret_cast<uint16_t*>(w);         w += align_up((size_t)n * 2, 256);
-  int* bad = reinterpret_cast<int*>(w);
+  uint16_t* lrank = reinterpret_cast<uint16_t*>(w);
   TPQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)nch * n_cells * 4, st));
-  TPQ_CUDA(cudaMemsetAsync(bad, 0, 4, st));
-  ioa_local_kernel<<<(unsigned)nch, 512, 0, st>>>(cells, n, n_cells, lrank, hist, bad);
+  ioa_local_kernel<<<(unsigned)nch, 512, 0, st>>>(cells, n, n_cells, lrank, hist);
   TPQ_LAUNCH_CHECK("ioa_local_kernel");
   ioa_scan_kernel<<<(n_cells + 255) / 256, 256, 0, st>>>(hist, (int)nch, n_cells, counts);
   TPQ_LAUNCH_CHECK("ioa_scan_kernel");
