@@ -831,9 +831,12 @@ def main():
         except Exception as e:
             secondary = {"error": repr(e)}
 
-    # our kernels per search: 2 x col_sqnorm, coarse_gemm, probe_select, ivfpq_scan, merge_topk
-    # (+ normalize_columns for cosine, + lut_scan when d/M is not 1/2/4/8, + the cross-shard merge(s) when sharded)
-    launches_per_step = 6 + (1 if distance == "cosine" else 0) + (0 if (d // M) in (1, 2, 4, 8) else 1) + (groups if world > 1 else 0)
+    # our kernels per step of the `value` loop: 2 x col_sqnorm, coarse_gemm, probe_select, ivfpq_scan (+ normalize_columns for
+    # cosine, + lut_scan when d/M is not 1/2/4/8), then one merge_topk on a single GPU; sharded: one merge_topk per query
+    # group, plus the rank-local merge/decode when the exchange is the NCCL all-gather (the fused push skips it).  The
+    # symmetric-memory barrier and NCCL kernels are torch's, not counted.
+    launches_per_step = 5 + (1 if distance == "cosine" else 0) + (0 if (d // M) in (1, 2, 4, 8) else 1)
+    launches_per_step += 1 if world == 1 else groups + (1 if args.exchange == "nccl" else 0)
     ach = rf["achieved_gbs"]
     line = {
         "metric": "queries/sec @ recall@100, IVFPQ search", "value": qps, "unit": "queries/s",
