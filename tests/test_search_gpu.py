@@ -361,3 +361,19 @@ def test_drop_reference_layout(cuda_device):
     assert torch.equal(v0, v1) and torch.equal(i0, i1)
     with pytest.raises(AssertionError):
         ix.add(queries(5).cuda())
+
+
+def test_empty_batch_and_empty_index(cuda_device):
+    """Edge cases: a batch of zero queries returns [0, k] tensors; an index that holds no vectors returns (-inf, -1)."""
+    import torchpq_b200 as T
+    st, queries = B.integer_state(32, 8, 8, 500, seed=3)
+    st.n_probe, st.use_smart_probing = 4, True
+    ix = make_index(st)
+    v, i = ix.search(torch.empty(32, 0, device="cuda"), k=5)
+    assert v.shape == (0, 5) and i.shape == (0, 5)
+    empty = T.IVFPQIndex(32, 8, 8, initial_size=16, device="cuda:0")
+    empty.vq_codec.set_codebook(torch.from_numpy(st.vq_codebook).cuda())
+    empty.pq_codec.set_codebook(torch.from_numpy(st.pq_codebook).cuda())
+    empty.n_probe = 4
+    v, i, a = empty.search(queries(9).cuda(), k=7, return_address=True)
+    assert torch.isinf(v).all() and (v < 0).all() and (i == -1).all() and (a == -1).all()
