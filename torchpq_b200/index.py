@@ -304,6 +304,8 @@ class IVFPQIndex(StateModule):
         ids = torch.empty(nq, k, dtype=torch.long, device=dev)
         address = torch.empty(nq, k, dtype=torch.long, device=dev) if return_address else None
         keys = torch.empty(nq, k, dtype=torch.int64, device=dev) if return_keys else None
+        if nq == 0:
+            return (values, ids) + ((address,) if return_address else ()) + ((keys,) if return_keys else ())
         ws_bytes = lib.tpq_search_workspace_bytes(C.byref(lay.cindex), nq, n_probe, k)
         ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
         if self.pq_use_residual:
