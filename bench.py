@@ -519,6 +519,17 @@ def secondary_block(device, threads, c3_index, c3_xs_dev, k3, steps):
             torch.cuda.empty_cache()
         except Exception as e:
             sec[name] = {"error": repr(e)}
+    # ---- batch-size sweep on the C3 index (also report nq in {1, 100, 1000}); small batches are cut into
+    #      slices so that every SM has work, the slices are merged by merge_topk_kernel
+    try:
+        sweep = {}
+        for nq_s in (1, 100, 1000):
+            xs_s = [x[:, :nq_s].contiguous() for x in c3_xs_dev]
+            ms = cuda_time(lambda i: c3_index.search(xs_s[i % 4], k=k3), 20, device=device)
+            sweep[str(nq_s)] = {"ms_per_batch": ms, "queries_per_s": nq_s / ms * 1e3}
+        sec["c3_batch_size_sweep"] = sweep
+    except Exception as e:
+        sec["c3_batch_size_sweep"] = {"error": repr(e)}
     # ---- residual IVFPQ (pq_use_residual=True) on the C3 shape, same queries
     try:
         wl = WORKLOADS["c3"]
